@@ -1,0 +1,167 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference here.
+
+TEST INFRASTRUCTURE ONLY; runs only in the build container (needs
+/root/reference).  Usage:  python oracle/gen_golden.py [scenario ...]
+
+Every fixture is produced by `/root/reference/src/environment/uav_env.py::
+UAVEnvironment` driven exactly like `sweep_eval.py::_greedy_worker` (:460-486):
+`random.seed(s); np.random.seed(s); env = UAVEnvironment(...); env.reset(seed=s)`.
+Because the reference's generators are all seedable and the numpy legacy stream
+is frozen across numpy versions, the fixture stores seeds + actions + outputs
+(not the ~1 kB/step of draws); `oracle/uavsim_oracle.py` in STREAM mode re-draws
+from the same generators in the same order, and a small sample of recorded
+draws is stored so that ordering itself is pinned.
+
+Two flavours (see oracle/ref_harness.py): `norm` = float32 log10 proxied to the
+correctly rounded value (host independent, compared bit-exactly), `raw` = numpy's
+own float32 log10 on this host (compared with the margin-aware checker).
+"""
+from __future__ import annotations
+
+import json
+import platform
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import ref_harness as H  # noqa: E402
+
+OUT = HERE.parent / "tests" / "golden"
+
+DENSE_KEYS = ("reward", "truncated", "pos", "battery", "sf", "visited", "capture_triggers",
+              "boundary_hits", "edge_steps", "last_step_bytes", "c_collision_count",
+              "c_urgency_reduced", "c_sensor_urgency", "c_was_new_sensor", "c_was_empty",
+              "c_all_sensors_collected", "c_bytes_collected", "c_data_loss",
+              "i_high_urgency_sensors", "i_sensors_collected")
+SPARSE_KEYS = ("buf", "gen", "tx", "lost", "ema", "obs", "i_ratios", "i_max_urgency",
+               "i_avg_urgency", "total_reward", "total_data_collected", "i_coverage_percentage",
+               "i_battery_percent")
+SPARSE_EVERY = 32
+DRAW_SAMPLE_STEPS = 12
+
+
+def _policy_random(seed, p_collect=None):
+    rng = np.random.default_rng(seed)
+
+    def pick(env, obs, t):
+        if p_collect is None:
+            return int(rng.integers(0, 5))
+        return 4 if rng.random() < p_collect else int(rng.integers(0, 4))
+    return pick
+
+
+def _policy_greedy(env):
+    agent = H.load_greedy_agents().NearestSensorGreedy(env)
+
+    def pick(env_, obs, t):
+        return int(agent.select_action(obs))
+    return pick
+
+
+def run_episode(sc, seed):
+    kw = dict(sc.get("env_kwargs", {}))
+    env = H.make_env(sc["grid"], sc["n"], seed=seed, start=sc.get("start"), **kw)
+    first = H.traced_reset(env, seed=seed)
+    if sc["policy"] == "greedy":
+        pick = _policy_greedy(env)
+    else:
+        pick = _policy_random(seed, sc.get("p_collect"))
+    steps, actions, burn = [], [], []
+    obs = first["obs"]
+    T = sc["steps"]
+    t = 0
+    while True:
+        before = H.REC.outside_normals
+        a = pick(env, obs, t)
+        burn.append(H.REC.outside_normals - before)
+        st = H.traced_step(env, a)
+        steps.append(st)
+        actions.append(a)
+        obs = st["obs"]
+        t += 1
+        if st["truncated"] or (T is not None and t >= T):
+            break
+    S = H.stack_steps(steps)
+    S["obs_sum"] = S["obs"].astype(np.float64).sum(axis=1)
+    sparse_idx = np.unique(np.concatenate([np.arange(0, t, SPARSE_EVERY), [t - 1]]))
+    out = {"actions": np.array(actions, dtype=np.int8), "burn": np.array(burn, dtype=np.int16),
+           "sparse_idx": sparse_idx.astype(np.int32),
+           "positions": np.array(env.sensor_positions, dtype=np.float64),
+           "reset_obs": first["obs"], "reset_fill": first["fill"], "reset_sf": first["sf"],
+           "reset_ema": first["ema"], "reset_buf": first["buf"],
+           "draws_head": np.concatenate([first["draws"][None], S["draws"][:DRAW_SAMPLE_STEPS]])}
+    for k in DENSE_KEYS + ("obs_sum",):
+        out[k] = S[k]
+    for k in SPARSE_KEYS:
+        out["sp_" + k] = S[k][sparse_idx]
+    return out
+
+
+SCENARIOS = {
+    # config 1: the reference's own CPU-runnable case
+    "c1_greedy_500_n20": dict(grid=(500, 500), n=20, policy="greedy", steps=None, seeds=list(range(20))),
+    # config 2 episodes (per-env seed = env id, uniform random actions); 4 of them to truncation
+    "c2_random_500_n20": dict(grid=(500, 500), n=20, policy="random", steps=320, seeds=list(range(24))),
+    "c2_random_500_n20_full": dict(grid=(500, 500), n=20, policy="random", steps=None, seeds=[0, 1, 2, 3]),
+    # config 5 geometry (1000x1000, N=50), collect-heavy so capture/collisions occur
+    "c5_mixed_1000_n50": dict(grid=(1000, 1000), n=50, policy="random", p_collect=0.5, steps=300,
+                              seeds=[0, 1, 2, 3]),
+    # dense small grid: many simultaneous transmitters (collisions, capture effect, drains)
+    "dense_100_n40": dict(grid=(100, 100), n=40, policy="random", p_collect=0.7, steps=400,
+                          start=(50.0, 50.0), seeds=list(range(6))),
+    # duty cycle 100 %: every in-range sensor transmits (stress for SF grouping / capture)
+    "duty100_200_n30": dict(grid=(200, 200), n=30, policy="random", p_collect=0.6, steps=300,
+                            start=(100.0, 100.0), seeds=[0, 1, 2],
+                            env_kwargs=dict(sensor_duty_cycle=100.0)),
+    # buffers saturate (data loss path) quickly: small buffer, long horizon handled by full episodes
+    "smallbuf_300_n10": dict(grid=(300, 300), n=10, policy="random", steps=400, seeds=[0, 1],
+                             env_kwargs=dict(max_buffer_size=400.0)),
+    # 5-feature observation variant (include_sensor_positions, uav_env.py:668-672)
+    "fps5_300_n12": dict(grid=(300, 300), n=12, policy="random", steps=120, seeds=[0, 1],
+                         env_kwargs=dict(include_sensor_positions=True)),
+    # collect duration != move duration (dt differs per action)
+    "cd2_200_n16": dict(grid=(200, 200), n=16, policy="random", p_collect=0.5, steps=200,
+                        start=(90.0, 110.0), seeds=[0, 1], env_kwargs=dict(collection_duration=2.0)),
+    # short battery: truncation by battery + terminal penalties within a short fixture
+    "lowbatt_200_n20": dict(grid=(200, 200), n=20, policy="random", p_collect=0.5, steps=None,
+                            start=(100.0, 100.0), seeds=[0, 1, 2], env_kwargs=dict(max_battery=30.0)),
+    # max_steps truncation
+    "maxsteps_150_n8": dict(grid=(150, 150), n=8, policy="random", steps=None, seeds=[0, 1],
+                            env_kwargs=dict(max_steps=150)),
+}
+
+
+def generate(name, flavour):
+    sc = SCENARIOS[name]
+    H.load_reference()
+    H.REC.normalise_log10 = (flavour == "norm")
+    blob = {}
+    for seed in sc["seeds"]:
+        ep = run_episode(sc, seed)
+        for k, v in ep.items():
+            blob["s%d/%s" % (seed, k)] = v
+    meta = dict(name=name, flavour=flavour, grid=list(sc["grid"]), n=sc["n"], seeds=sc["seeds"],
+                policy=sc["policy"], start=list(sc.get("start") or (0.0, 0.0)),
+                env_kwargs=sc.get("env_kwargs", {}), sparse_every=SPARSE_EVERY,
+                numpy=np.__version__, python=platform.python_version(), machine=platform.machine(),
+                generator="oracle/gen_golden.py", reference_entry="src/environment/uav_env.py::UAVEnvironment")
+    blob["meta"] = np.array(json.dumps(meta))
+    OUT.mkdir(parents=True, exist_ok=True)
+    path = OUT / ("%s.%s.npz" % (name, flavour))
+    np.savez_compressed(path, **blob)
+    print("%-36s %-4s %7.1f kB  steps/seed=%s" % (
+        name, flavour, path.stat().st_size / 1e3,
+        [int(blob["s%d/actions" % s].shape[0]) for s in sc["seeds"]][:6]))
+
+
+RAW_TOO = ("c1_greedy_500_n20",)
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SCENARIOS)
+    for nm in names:
+        generate(nm, "norm")
+        if nm in RAW_TOO:
+            generate(nm, "raw")

@@ -1,0 +1,316 @@
+"""Harness that runs the UNMODIFIED reference environment in this container.
+
+TEST INFRASTRUCTURE ONLY (golden-vector generation).  Nothing in the product
+imports this file and it cannot run on the GPU box: /root/reference exists only
+in the build container.  `oracle/gen_golden.py` uses it to write
+`tests/golden/*.npz`.
+
+What it does
+------------
+* puts stub `gymnasium` / `matplotlib` packages (oracle/_stubs) on sys.path and
+  imports `/root/reference/src/environment/uav_env.py` in place (read-only
+  mount, so bytecode writing is disabled);
+* installs *recording proxies* -- no reference source is edited:
+    - `iot_sensors.np`      -> proxy whose `random.normal` records every
+                               shadowing draw (`iot_sensors.py:192`) and whose
+                               `log10` can optionally be normalised to the
+                               correctly-rounded float32 result (see below);
+    - `uav_env.random`      -> proxy whose `random()` records the duty-cycle
+                               uniforms (`uav_env.py:549`);
+    - `gymnasium.Env._uniform_tap` -> records the buffer-fill uniforms
+                               (`uav_env.py:410`);
+    - `IoTSensor.update_spreading_factor / get_success_probability /
+      is_in_range` and `UAVEnvironment._get_observation` are wrapped to tag each
+      draw with its SLOT (A,B,U,C,D,E of SURVEY.md section 3.2) and sensor id;
+    - `RewardFunction.calculate_collection_reward` is wrapped to capture the
+      collect step's intermediate quantities (collision count, bytes, ...).
+
+log10 normalisation
+-------------------
+numpy's float32 `log10` is not correctly rounded and depends on the host's SIMD
+dispatch (61 % of inputs differ by one ulp on an AVX-512 host).  With
+`normalise_log10=True` the proxy returns `float32(log10(float64(x)))` for
+float32 inputs, which is host independent; the oracle and the CUDA kernels use
+that definition.  Goldens are generated in both flavours.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+
+REFERENCE_ROOT = Path(os.environ.get("UAVSIM_REFERENCE_ROOT", "/root/reference"))
+_STUBS = Path(__file__).resolve().parent / "_stubs"
+
+SLOT_A, SLOT_B, SLOT_U, SLOT_C, SLOT_D, SLOT_E = range(6)
+NUM_SLOTS = 6
+
+
+def reference_available() -> bool:
+    return (REFERENCE_ROOT / "src" / "environment" / "uav_env.py").is_file()
+
+
+class _Recorder:
+    """Collects the draws of the env step currently being executed."""
+
+    def __init__(self):
+        self.in_env = False      # inside env.reset()/env.step()
+        self.in_obs = False      # inside _get_observation()
+        self.ctx = None          # (sensor_id, slot) for the next normal draw
+        self.num_sensors = 0
+        self.draws = None        # [6, N] float64, NaN = not drawn
+        self.fill = []           # buffer-fill uniforms of the current reset
+        self.outside_normals = 0 # draws consumed outside env.step/reset (agents)
+        self.collect_kwargs = None
+        self.normalise_log10 = False
+
+    def begin(self, n):
+        self.num_sensors = n
+        self.draws = np.full((NUM_SLOTS, n), np.nan, dtype=np.float64)
+        self.collect_kwargs = None
+        self.in_env = True
+
+    def end(self):
+        self.in_env = False
+        self.ctx = None
+
+    def on_normal(self, v):
+        if not self.in_env:
+            self.outside_normals += 1
+            return
+        sid, slot = self.ctx
+        assert np.isnan(self.draws[slot, sid]), ("slot drawn twice", slot, sid)
+        self.draws[slot, sid] = v
+        self.ctx = None
+
+    def on_uniform01(self, v):
+        assert self.in_env
+        sid = self._last_sensor
+        assert np.isnan(self.draws[SLOT_U, sid])
+        self.draws[SLOT_U, sid] = v
+
+
+REC = _Recorder()
+_loaded = {}
+
+
+class _RandomNormalProxy:
+    def __init__(self, real_random):
+        self._real = real_random
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        v = self._real.normal(loc, scale, size)
+        assert size is None and loc == 0
+        REC.on_normal(float(v))
+        return v
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+class _NumpyProxy:
+    """Stands in for the name `np` inside the reference's iot_sensors module."""
+
+    def __init__(self, real):
+        self._real = real
+        self.random = _RandomNormalProxy(real.random)
+
+    def log10(self, x):
+        if REC.normalise_log10 and isinstance(x, self._real.float32):
+            return self._real.float32(self._real.log10(self._real.float64(x)))
+        return self._real.log10(x)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+class _PyRandomProxy:
+    def __init__(self, real):
+        self._real = real
+
+    def random(self):
+        v = self._real.random()
+        REC.on_uniform01(v)
+        return v
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+def load_reference():
+    """Import the reference modules (once) and install the recording proxies."""
+    if _loaded:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    sys.dont_write_bytecode = True
+    src = REFERENCE_ROOT / "src"
+    for p in (str(_STUBS), str(src), str(src / "environment")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gymnasium  # the stub
+    import iot_sensors  # reference, unmodified
+    import uav as uav_mod
+    import uav_env
+    import random as py_random
+
+    iot_sensors.np = _NumpyProxy(np)
+    uav_env.random = _PyRandomProxy(py_random)
+    gymnasium.Env._uniform_tap = staticmethod(lambda v: REC.fill.append(float(v)))
+
+    S = iot_sensors.IoTSensor
+    E = uav_env.UAVEnvironment
+    o_usf, o_gsp, o_iir = S.update_spreading_factor, S.get_success_probability, S.is_in_range
+    o_obs = E._get_observation
+
+    def usf(self, uav_position, current_step=0):
+        REC.ctx = (self.sensor_id, SLOT_D if REC.in_obs else SLOT_A)
+        return o_usf(self, uav_position, current_step)
+
+    def gsp(self, uav_position, use_advanced_model=True):
+        REC.ctx = (self.sensor_id, SLOT_B if use_advanced_model else SLOT_C)
+        REC._last_sensor = self.sensor_id
+        return o_gsp(self, uav_position, use_advanced_model)
+
+    def iir(self, uav_position):
+        REC.ctx = (self.sensor_id, SLOT_E)
+        return o_iir(self, uav_position)
+
+    def obs(self):
+        REC.in_obs = True
+        try:
+            return o_obs(self)
+        finally:
+            REC.in_obs = False
+
+    S.update_spreading_factor, S.get_success_probability, S.is_in_range = usf, gsp, iir
+    E._get_observation = obs
+
+    from rewards import reward_function as rf_mod
+    o_ccr = rf_mod.RewardFunction.calculate_collection_reward
+
+    def ccr(self, **kw):
+        REC.collect_kwargs = dict(kw)
+        return o_ccr(self, **kw)
+
+    rf_mod.RewardFunction.calculate_collection_reward = ccr
+
+    _loaded.update(dict(uav_env=uav_env, iot_sensors=iot_sensors, uav=uav_mod,
+                        UAVEnvironment=E, IoTSensor=S, py_random=py_random,
+                        gymnasium=gymnasium))
+    return _loaded
+
+
+def load_greedy_agents():
+    """Import the reference's greedy drivers (used unmodified for config 1)."""
+    mods = load_reference()
+    if "greedy" not in mods:
+        p = str(REFERENCE_ROOT / "src" / "agents" / "dqn" / "dqn_evaluation_results")
+        if p not in sys.path:
+            sys.path.insert(0, p)
+        # greedy_agents.py does `from environment.uav_env import UAVEnvironment`;
+        # alias the already-imported module so the proxies stay in force.
+        pkg = types.ModuleType("environment")
+        pkg.__path__ = [str(REFERENCE_ROOT / "src" / "environment")]
+        sys.modules.setdefault("environment", pkg)
+        sys.modules.setdefault("environment.uav_env", mods["uav_env"])
+        sys.modules.setdefault("environment.iot_sensors", mods["iot_sensors"])
+        import greedy_agents
+        mods["greedy"] = greedy_agents
+    return mods["greedy"]
+
+
+# --------------------------------------------------------------------------
+# state snapshots
+# --------------------------------------------------------------------------
+def snapshot(env) -> dict:
+    """Everything SURVEY.md section 8a lists as persistent state, as arrays."""
+    n = env.num_sensors
+    s = env.sensors
+    out = dict(
+        pos=np.asarray(env.uav.position, dtype=np.float32).copy(),
+        battery=np.float64(env.uav.battery),
+        step=np.int32(env.current_step),
+        buf=np.array([x.data_buffer for x in s], dtype=np.float64),
+        gen=np.array([x.total_data_generated for x in s], dtype=np.float64),
+        tx=np.array([x.total_data_transmitted for x in s], dtype=np.float64),
+        lost=np.array([x.total_data_lost for x in s], dtype=np.float64),
+        ema=np.array([np.nan if x.avg_rssi is None else x.avg_rssi for x in s], dtype=np.float64),
+        sf=np.array([x.spreading_factor for x in s], dtype=np.int8),
+        visited=np.array([i in env.sensors_visited for i in range(n)], dtype=np.bool_),
+        total_reward=np.float64(env.total_reward),
+        total_data_collected=np.float64(env.total_data_collected),
+        capture_triggers=np.int32(env.capture_effect_triggers),
+        boundary_hits=np.int32(env.boundary_hits),
+        edge_steps=np.int32(env.edge_steps),
+        last_step_bytes=np.float64(env.last_step_bytes_collected),
+    )
+    return out
+
+
+INFO_SCALARS = ("max_urgency", "avg_urgency", "high_urgency_sensors", "coverage_percentage",
+                "battery_percent", "sensors_collected")
+
+COLLECT_KEYS = ("bytes_collected", "was_new_sensor", "was_empty", "all_sensors_collected",
+                "battery_used", "collision_count", "data_loss", "urgency_reduced",
+                "sensor_urgency")
+
+
+def make_env(grid, num_sensors, seed=None, sensor_positions=None, start=None, **kw):
+    """Construct the reference env the way `sweep_eval.py:460-463` does."""
+    mods = load_reference()
+    if seed is not None:
+        mods["py_random"].seed(seed)
+        np.random.seed(seed)
+    kwargs = dict(max_steps=2100, path_loss_exponent=3.8, rssi_threshold=-85.0,
+                  sensor_duty_cycle=10.0)
+    kwargs.update(kw)
+    if sensor_positions is not None:
+        kwargs["sensor_positions"] = [tuple(map(float, p)) for p in sensor_positions]
+    if start is not None:
+        kwargs["uav_start_position"] = tuple(map(float, start))
+    return mods["UAVEnvironment"](grid_size=tuple(grid), num_sensors=num_sensors, **kwargs)
+
+
+def traced_reset(env, seed=None):
+    REC.fill = []
+    REC.begin(env.num_sensors)
+    try:
+        obs, info = env.reset(seed=seed)
+    finally:
+        REC.end()
+    st = snapshot(env)
+    st["obs"] = np.asarray(obs, dtype=np.float32)
+    st["draws"] = REC.draws.copy()
+    st["fill"] = np.array(REC.fill, dtype=np.float64)
+    st["info"] = info
+    return st
+
+
+def traced_step(env, action):
+    REC.begin(env.num_sensors)
+    try:
+        obs, reward, terminated, truncated, info = env.step(int(action))
+    finally:
+        REC.end()
+    st = snapshot(env)
+    st["obs"] = np.asarray(obs, dtype=np.float32)
+    st["reward"] = np.float64(reward)
+    st["truncated"] = np.bool_(truncated)
+    st["terminated"] = np.bool_(terminated)
+    st["draws"] = REC.draws.copy()
+    ck = REC.collect_kwargs
+    for k in COLLECT_KEYS:
+        st["c_" + k] = np.float64(ck[k]) if ck is not None else np.float64(np.nan)
+    for k in INFO_SCALARS:
+        st["i_" + k] = np.float64(info[k])
+    st["i_ratios"] = np.array(info["sensor_collection_ratios"], dtype=np.float64)
+    return st
+
+
+def stack_steps(steps: list) -> dict:
+    keys = [k for k in steps[0] if k != "info"]
+    return {k: np.stack([s[k] for s in steps]) for k in keys}

@@ -1,0 +1,297 @@
+/*
+ * uavsim.h -- C ABI of the B200-native batched UAV-LoRa environment step.
+ *
+ * This is the drop-in boundary for ONE path of the reference project
+ * (atiladeokegab/...-UAV-...-IoT-Sensor-Networks): the Gymnasium environment
+ *     src/environment/uav_env.py::UAVEnvironment.reset / .step   (:400-427, :429-488)
+ * together with the objects it drives
+ *     src/environment/uav.py::UAV                 (:63-263)
+ *     src/environment/iot_sensors.py::IoTSensor   (:10-321)
+ *     src/rewards/reward_function.py::RewardFunction (:4-128)
+ * and the per-env training wrapper
+ *     src/agents/dqn/dqn.py::DomainRandEnv        (:177-451)
+ * as consumed through stable-baselines3's VecEnv (dqn.py:1276-1278).
+ *
+ * The reference is pure Python and has no FFI of its own; the binding a
+ * maintainer would add is the ctypes loader shown in INTEGRATION.md (and shipped
+ * as <package>/_native.py).  Everything here is plain C: pointers, sizes and
+ * POD structs, no C++ or torch types.  All device work is stream-ordered on the
+ * stream the caller passes (a cudaStream_t as void*); no entry point
+ * synchronises unless its comment says so.  One host thread per handle.  The
+ * device is the one current (cudaSetDevice) when uavsim_create is called.
+ *
+ * Every function returns UAVSIM_OK (0) or a negative uavsim_status;
+ * uavsim_last_error() gives the message for the calling thread.
+ */
+#ifndef UAVSIM_H_
+#define UAVSIM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVSIM_ABI_VERSION 1
+#define UAVSIM_MAX_SENSORS 64 /* visited set is one 64-bit word; the reference tops out at 50 (dqn.py:121) */
+#define UAVSIM_MAX_GRIDS 8    /* grids per curriculum stage (dqn.py:63-69 uses <= 5) */
+#define UAVSIM_NUM_SLOTS 6    /* replay draw slots A,B,U,C,D,E */
+#define UAVSIM_NUM_ACTIONS 5  /* uav_env.py:347  Discrete(5): UP, DOWN, LEFT, RIGHT, COLLECT */
+
+typedef enum uavsim_status {
+    UAVSIM_OK = 0,
+    UAVSIM_ERR_INVALID_ARG = -1,
+    UAVSIM_ERR_CUDA = -2,
+    UAVSIM_ERR_STATE = -3,          /* call order (e.g. step before outputs are bound) */
+    UAVSIM_ERR_INVALID_ACTION = -4, /* an action outside [0,4] was seen (uav_env.py:468 raises ValueError) */
+    UAVSIM_ERR_UNSUPPORTED = -5
+} uavsim_status;
+
+typedef enum uavsim_precision {
+    UAVSIM_F64 = 0, /* parity layout: float64 accumulators like the reference, IEEE op order, no FMA contraction */
+    UAVSIM_F32 = 1  /* throughput layout: float32 state, fast intrinsics */
+} uavsim_precision;
+
+typedef enum uavsim_rng_mode {
+    UAVSIM_RNG_REPLAY = 0, /* every random draw is read from a slot-addressed table bound with uavsim_set_replay */
+    UAVSIM_RNG_PHILOX = 1  /* counter-based Philox4x32-10 keyed by (seed; global env id, episode, step, sensor, slot) */
+} uavsim_rng_mode;
+
+typedef enum uavsim_reset_mode {
+    UAVSIM_RESET_FIXED = 0,      /* UAVEnvironment: layout + start fixed at construction, buffers refilled U(0.2,0.6) (uav_env.py:400-427) */
+    UAVSIM_RESET_DOMAIN_RAND = 1 /* DomainRandEnv: new grid from the stage list, new uniform layout, empty fresh sensors,
+                                    far-start rejection sampling, proximity + Jain shaping (dqn.py:301-444) */
+} uavsim_reset_mode;
+
+/* Replay draw slots.  A/B/U are consumed per sensor with data on a COLLECT
+ * step (ADR draw, link-probability draw, duty-cycle uniform), C by each SF-group
+ * winner (range check in collect_data), D/E per sensor by every observation
+ * (ADR draw, range draw).  Normal slots hold the shadowing value itself, i.e.
+ * the result of np.random.normal(0, shadowing_std_db) (iot_sensors.py:192);
+ * U holds random.random() (uav_env.py:549). */
+enum { UAVSIM_SLOT_A = 0, UAVSIM_SLOT_B = 1, UAVSIM_SLOT_U = 2, UAVSIM_SLOT_C = 3, UAVSIM_SLOT_D = 4, UAVSIM_SLOT_E = 5 };
+
+typedef struct uavsim_config {
+    uint32_t struct_size; /* = sizeof(uavsim_config); checked by uavsim_create */
+    int32_t num_envs;     /* E, environments owned by this handle (one device) */
+    int32_t max_sensors;  /* P, sensor slots per env row (>= every env's N, <= UAVSIM_MAX_SENSORS) */
+    int32_t obs_slots;    /* sensor slots in the observation row (zero padded; 50 for the attention extractor, dqn.py:121,567-571) */
+    int32_t features_per_sensor; /* 3, or 5 with include_sensor_positions (uav_env.py:349,668-672) */
+    int32_t frame_stack;  /* k frames kept per env, newest last (VecFrameStack, dqn.py:1278); 1 = none */
+    int32_t precision;    /* uavsim_precision */
+    int32_t rng_mode;     /* uavsim_rng_mode */
+    int32_t reset_mode;   /* uavsim_reset_mode */
+    int32_t auto_reset;   /* 1: SB3 VecEnv semantics -- a finished env is reset inside the same step call,
+                             obs holds the new episode's first observation and terminal_obs the last one */
+    uint64_t seed;        /* Philox key */
+    int64_t env_id_offset; /* global id of local env 0: RNG streams do not depend on how envs are sharded */
+
+    /* --- environment constructor arguments (uav_env.py:266-287) --- */
+    int32_t grid_w, grid_h;      /* default grid for every env (FIXED mode); per-env override via uavsim_set_scenario */
+    int32_t num_sensors;         /* default N for every env; per-env override via uavsim_set_scenario */
+    int32_t max_steps;           /* 2100 on the training/eval path (dqn.py:1069) */
+    double data_generation_rate; /* 2.2 B/s */
+    double max_buffer_size;      /* 1000 B */
+    double rssi_threshold;       /* -85 dBm */
+    double duty_cycle;           /* percent, 10 */
+    double max_battery;          /* 274 Wh */
+    double collection_duration;  /* 1 s */
+    double start_x, start_y;     /* uav_start_position, default (0,0) (uav_env.py:332-333) */
+
+    /* --- IoTSensor / UAV constants (iot_sensors.py:39-57, uav.py:88-125) --- */
+    double tx_power_dbm;         /* 14 */
+    double noise_floor_dbm;      /* -105 */
+    double altitude_m;           /* 100 */
+    double adr_lambda;           /* 0.1 */
+    double shadowing_std_db;     /* 4 */
+    double capture_threshold_db; /* 6 (uav_env.py:569) */
+    double power_move_w;         /* 500 */
+    double power_hover_w;        /* 700 */
+    int32_t init_sf;             /* 12: IoTSensor.reset forces SF12 (iot_sensors.py:309) */
+    int32_t reserved0;
+
+    /* --- RewardFunction (reward_function.py:7-44 with the overrides of uav_env.py:339-344) --- */
+    double reward_per_byte, reward_new_sensor, reward_completion, reward_urgency_reduction, reward_movement;
+    double penalty_revisit, penalty_boundary, penalty_collision, penalty_battery, penalty_hover, penalty_step;
+    double penalty_data_loss, penalty_starvation, penalty_unvisited, penalty_starved, starvation_cr_threshold;
+
+    /* --- DomainRandEnv (dqn.py:63-69, 126-130, 415-444) --- */
+    int32_t num_grids;                   /* grids of the current curriculum stage */
+    int32_t grids[UAVSIM_MAX_GRIDS][2];
+    double min_start_dist;               /* 50 */
+    int32_t max_start_tries;             /* 200 */
+    int32_t reserved1;
+    double prox_eta;                     /* 2.0 */
+    double jain_bonus;                   /* 0.5: reward += jain_bonus*(J-0.5)/N */
+} uavsim_config;
+
+/* State columns visible through uavsim_get_field (structure-of-arrays in HBM). */
+typedef enum uavsim_field {
+    UAVSIM_FIELD_ENV_RECORD = 0,  /* [E] uavsim_env_record (128 B each) */
+    UAVSIM_FIELD_SENSOR_STATE = 1,/* [E][P][4] real: buffer, transmitted, lost, avg_rssi (NaN = None) */
+    UAVSIM_FIELD_SENSOR_POS = 2,  /* [E][P][2] float32 */
+    UAVSIM_FIELD_SENSOR_GEN = 3,  /* [E][P] real: F64: total_data_generated; F32: its value at reset (generated = this + rate*elapsed) */
+    UAVSIM_FIELD_SENSOR_SF = 4,   /* [E][P] uint8 spreading factor 7..12 */
+    UAVSIM_FIELD_COUNT = 5
+} uavsim_field;
+
+/* Per-environment scalars, one 128-byte record per env (same in both precisions). */
+typedef struct uavsim_env_record {
+    float x, y;                 /* uav.position (float32, uav.py:113) */
+    float start_x, start_y;     /* uav.start_position */
+    double battery;             /* Wh */
+    double total_reward;        /* env.total_reward (uav_env.py:487; base reward, no wrapper shaping) */
+    double total_data_collected;
+    double episode_return;      /* what Monitor would report: base reward + DomainRandEnv shaping */
+    float last_step_bytes;
+    float prev_dist_nearest;    /* DomainRandEnv._prev_dist_nearest */
+    float elapsed_s;            /* sum of step durations this episode */
+    int32_t step;               /* current_step */
+    int32_t grid_w, grid_h;
+    int32_t num_sensors;        /* N */
+    uint32_t visited_lo, visited_hi; /* sensors_visited as a bit set */
+    int32_t capture_triggers;
+    int32_t boundary_hits;
+    int32_t edge_steps;
+    int32_t collisions;         /* cumulative collision_count */
+    int32_t first_full_coverage_step; /* -1 = not yet (dqn.py:428-431) */
+    uint32_t episode;           /* episodes completed by this env (RNG counter word) */
+    int32_t delivered;          /* cumulative successful transmissions (iot_sensors.py:141-143) */
+    int32_t reserved[4];
+} uavsim_env_record;
+
+typedef struct uavsim_field_view {
+    void* ptr;              /* device pointer */
+    int32_t elem_bytes;     /* bytes per scalar element */
+    int32_t is_float;       /* 1 float, 0 integer, 2 = struct record */
+    int32_t ndim;
+    int64_t shape[4];
+    int64_t stride_bytes[4];
+} uavsim_field_view;
+
+/* Per-episode statistics row written when an env finishes (DomainRandEnv.last_episode_stats,
+ * dqn.py:316-331, plus Monitor's r/l).  Index into a float64[UAVSIM_STAT_COUNT] row. */
+enum {
+    UAVSIM_STAT_RETURN = 0, UAVSIM_STAT_LENGTH = 1, UAVSIM_STAT_TOTAL_GENERATED = 2,
+    UAVSIM_STAT_TOTAL_COLLECTED = 3, UAVSIM_STAT_TOTAL_LOST = 4, UAVSIM_STAT_BATTERY_REMAINING = 5,
+    UAVSIM_STAT_NDR = 6, UAVSIM_STAT_FAIRNESS_STD = 7, UAVSIM_STAT_JAINS = 8, UAVSIM_STAT_GRID_W = 9,
+    UAVSIM_STAT_GRID_H = 10, UAVSIM_STAT_NUM_SENSORS = 11, UAVSIM_STAT_DATA_EFFICIENCY = 12,
+    UAVSIM_STAT_BYTES_PER_WH = 13, UAVSIM_STAT_TIME_TO_COVERAGE = 14, UAVSIM_STAT_CAPTURE_TRIGGERS = 15,
+    UAVSIM_STAT_BOUNDARY_HITS = 16, UAVSIM_STAT_EDGE_STEPS = 17, UAVSIM_STAT_COLLISIONS = 18,
+    UAVSIM_STAT_BASE_RETURN = 19, UAVSIM_STAT_COUNT = 20
+};
+/* Device-side running sums over finished episodes (payload of the one NCCL all-reduce):
+ * float64[UAVSIM_STAT_COUNT + 1]; element 0..COUNT-1 = sum of the stat, element COUNT = episodes finished. */
+#define UAVSIM_STAT_SUMS (UAVSIM_STAT_COUNT + 1)
+
+/* Output buffers, allocated by the caller (e.g. torch tensors -> zero-copy), borrowed by the library.
+ * reward dtype follows precision (float64 / float32).  Nullable members are optional. */
+typedef struct uavsim_outputs {
+    float* obs;            /* [E][frame_stack_rows][obs_dim]; see uavsim_query_dims */
+    void* reward;          /* [E] real */
+    uint8_t* done;         /* [E] terminated|truncated (terminated is always false in the reference, uav_env.py:471) */
+    float* terminal_obs;   /* [E][obs_dim] last observation of a finished episode (auto_reset), nullable */
+    double* episode_stats; /* [E][UAVSIM_STAT_COUNT] written when an env finishes, nullable */
+    uint8_t* action_mask;  /* [E] bit a set = action a valid (derived: uav.py:175; COLLECT always), nullable */
+    double* step_detail;   /* [E][UAVSIM_DETAIL_COUNT] per-step diagnostics for parity tests, nullable */
+    void* draw_export;     /* [E][6][P] real: draws actually used this step (Philox mode), nullable */
+} uavsim_outputs;
+
+enum {
+    UAVSIM_DETAIL_COLLISIONS = 0, UAVSIM_DETAIL_BYTES = 1, UAVSIM_DETAIL_URGENCY_REDUCED = 2,
+    UAVSIM_DETAIL_MEAN_URGENCY = 3, UAVSIM_DETAIL_WAS_NEW = 4, UAVSIM_DETAIL_WAS_EMPTY = 5,
+    UAVSIM_DETAIL_ALL_COLLECTED = 6, UAVSIM_DETAIL_DATA_LOSS = 7, UAVSIM_DETAIL_ATTEMPT_MASK_LO = 8,
+    UAVSIM_DETAIL_ATTEMPT_MASK_HI = 9, UAVSIM_DETAIL_WINNER_MASK_LO = 10, UAVSIM_DETAIL_WINNER_MASK_HI = 11,
+    UAVSIM_DETAIL_BASE_REWARD = 12, UAVSIM_DETAIL_TRUNCATED = 13, UAVSIM_DETAIL_COUNT = 16
+};
+
+typedef struct uavsim_dims {
+    int32_t obs_dim;        /* 3 + features_per_sensor*obs_slots */
+    int32_t obs_row_floats; /* floats per env in outputs.obs (= frame rows * obs_dim) */
+    int32_t frame_rows;     /* physical frame rows per env (2k-1 mirrored ring when frame_stack>1, else 1) */
+    int32_t real_bytes;     /* 8 or 4 */
+    int64_t arena_bytes;    /* device bytes uavsim_create needs for all state */
+    int64_t replay_step_doubles;  /* doubles per env in a replay draw table: 6*P */
+} uavsim_dims;
+
+/* Injected scenario (per env).  All device pointers, nullable = keep. */
+typedef struct uavsim_scenario {
+    const float* sensor_xy;     /* [E][P][2]; rows beyond an env's N ignored */
+    const int32_t* num_sensors; /* [E] */
+    const int32_t* grid_wh;     /* [E][2] */
+    const float* start_xy;      /* [E][2] */
+} uavsim_scenario;
+
+/* Replay tables (UAVSIM_RNG_REPLAY).  All device pointers to float64.
+ * step_draws: draws of the step about to run, [E][6][P].
+ * reset_draws/reset_fill: consumed by uavsim_reset and by in-step auto-reset:
+ *   reset_draws [E][6][P] (only slots D,E read), reset_fill [E][P] = np_random.uniform(0.2,0.6)
+ *   (uav_env.py:410).  reset_init_sf [E] int32 (DomainRand: SF inherited from the old sensor 0,
+ *   dqn.py:345-353), nullable -> config.init_sf.
+ * reset_scenario: layout/grid/start the reset installs (DomainRand), nullable members keep. */
+typedef struct uavsim_replay {
+    const double* step_draws;
+    const double* reset_draws;
+    const double* reset_fill;
+    const int32_t* reset_init_sf;
+    uavsim_scenario reset_scenario;
+} uavsim_replay;
+
+typedef struct uavsim_handle uavsim_handle;
+
+/* ---- host-only helpers (no device needed) -------------------------------- */
+int uavsim_abi_version(void);
+/* Fills *cfg with the reference's training-path defaults (SURVEY.md section 8 header). */
+int uavsim_default_config(uavsim_config* cfg);
+/* Validates cfg and reports sizes.  Pure host arithmetic. */
+int uavsim_query_dims(const uavsim_config* cfg, uavsim_dims* out);
+const char* uavsim_last_error(void);
+
+/* ---- lifecycle ------------------------------------------------------------ */
+/* arena_dev: device memory of at least dims.arena_bytes, 256-byte aligned, owned by the caller
+ * (torch allocates, the library borrows); NULL -> the library cudaMallocs (and frees) its own.
+ * Zero-fills the arena on `stream`. */
+int uavsim_create(const uavsim_config* cfg, void* arena_dev, size_t arena_bytes, void* stream,
+                  uavsim_handle** out);
+int uavsim_destroy(uavsim_handle* h);
+int uavsim_bind_outputs(uavsim_handle* h, const uavsim_outputs* out, void* stream);
+int uavsim_get_field(uavsim_handle* h, int field, uavsim_field_view* out);
+
+/* ---- scenario / replay ---------------------------------------------------- */
+/* Install injected layouts etc. (replaces `sensor_positions=` / `uav_start_position=` ctor args). */
+int uavsim_set_scenario(uavsim_handle* h, const uavsim_scenario* sc, void* stream);
+/* Generate per-env uniform layouts with Philox, np.random.uniform([0,0],[W,H]) in distribution
+ * (uav_env.py:366-374).  FIXED mode construction when no layout is injected. */
+int uavsim_generate_layouts(uavsim_handle* h, void* stream);
+int uavsim_set_replay(uavsim_handle* h, const uavsim_replay* rp);
+/* DomainRandEnv.set_curriculum_stage (dqn.py:258-277): the grid list later resets sample from. */
+int uavsim_set_stage_grids(uavsim_handle* h, int32_t num_grids, const int32_t* grids_wh);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* Gymnasium reset for the envs whose mask byte is non-zero (NULL = all): uav_env.py:400-427 /
+ * dqn.py:301-372.  Writes obs (and action_mask). */
+int uavsim_reset(uavsim_handle* h, const uint8_t* env_mask_dev, void* stream);
+/* One environment step for every env: uav_env.py:429-488 (+ dqn.py:415-444 in DOMAIN_RAND mode).
+ * actions_dev: [E] int32 in [0,4].  Writes obs, reward, done (+ optional outputs). */
+int uavsim_step(uavsim_handle* h, const int32_t* actions_dev, void* stream);
+/* Same step with HOST buffers: copies actions host->device, steps, copies obs/reward/done back,
+ * all on `stream`, then synchronises the stream.  Buffers should be pinned for full PCIe rate.
+ * obs_host may be NULL to skip that copy. */
+int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_host, void* reward_host,
+                     uint8_t* done_host, void* stream);
+
+/* ---- diagnostics ---------------------------------------------------------- */
+/* Synchronises `stream`, then reports and clears the device error word: returns
+ * UAVSIM_ERR_INVALID_ACTION if any env saw an action outside [0,4] since the last poll
+ * (*first_env = lowest such local env id of the first offending step, nullable). */
+int uavsim_poll_error(uavsim_handle* h, void* stream, int64_t* first_env);
+/* float64[UAVSIM_STAT_SUMS] device array of running episode-stat sums (all-reduce payload). */
+int uavsim_stat_sums(uavsim_handle* h, double** sums_dev);
+/* Kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t uavsim_launch_count(const uavsim_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVSIM_H_ */

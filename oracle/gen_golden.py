@@ -12,9 +12,10 @@ is frozen across numpy versions, the fixture stores seeds + actions + outputs
 from the same generators in the same order, and a small sample of recorded
 draws is stored so that ordering itself is pinned.
 
-Two flavours (see oracle/ref_harness.py): `norm` = float32 log10 proxied to the
-correctly rounded value (host independent, compared bit-exactly), `raw` = numpy's
-own float32 log10 on this host (compared with the margin-aware checker).
+Two flavours (see oracle/ref_harness.py): `norm` = the two host-ISA dependent
+float32 operations (log10, scalar **2) proxied to their correctly rounded values
+(host independent, compared bit-exactly), `raw` = numpy's own SIMD routines on this
+host (compared with the margin-aware checker).
 """
 from __future__ import annotations
 
@@ -137,7 +138,7 @@ SCENARIOS = {
 def generate(name, flavour):
     sc = SCENARIOS[name]
     H.load_reference()
-    H.REC.normalise_log10 = (flavour == "norm")
+    H.REC.normalise = (flavour == "norm")
     blob = {}
     for seed in sc["seeds"]:
         ep = run_episode(sc, seed)

@@ -25,13 +25,17 @@ What it does
     - `RewardFunction.calculate_collection_reward` is wrapped to capture the
       collect step's intermediate quantities (collision count, bytes, ...).
 
-log10 normalisation
--------------------
-numpy's float32 `log10` is not correctly rounded and depends on the host's SIMD
-dispatch (61 % of inputs differ by one ulp on an AVX-512 host).  With
-`normalise_log10=True` the proxy returns `float32(log10(float64(x)))` for
-float32 inputs, which is host independent; the oracle and the CUDA kernels use
-that definition.  Goldens are generated in both flavours.
+float32 normalisation
+---------------------
+Two float32 elementary operations inside `calculate_rssi` (iot_sensors.py:163-167,
+179-183) are host-ISA dependent in numpy: `np.log10(float32)` (AVX-512 SIMD loop: 62 %
+of inputs differ by one ulp from the correctly rounded value) and the scalar power
+`float32 ** 2` (routed through the same SIMD `power` loop: 0.07 % of inputs differ by
+one ulp from `x*x`).  With `REC.normalise = True` the proxies make both correctly
+rounded and host independent -- `log10` returns `float32(log10(float64(x)))`, and the
+float32 scalars inside `calculate_rssi` are a float32 subclass whose `** 2` is `x*x`
+-- without touching the reference source.  The oracle and the CUDA kernels use those
+definitions.  Goldens are generated in both flavours (`norm`, `raw`).
 """
 from __future__ import annotations
 
@@ -65,7 +69,7 @@ class _Recorder:
         self.fill = []           # buffer-fill uniforms of the current reset
         self.outside_normals = 0 # draws consumed outside env.step/reset (agents)
         self.collect_kwargs = None
-        self.normalise_log10 = False
+        self.normalise = False
 
     def begin(self, n):
         self.num_sensors = n
@@ -111,6 +115,24 @@ class _RandomNormalProxy:
         return getattr(self._real, name)
 
 
+class N32(np.float32):
+    """float32 scalar whose arithmetic stays N32 and whose `** 2` is the correctly
+    rounded product (see module docstring).  Only the operators calculate_rssi uses."""
+
+    def __sub__(self, o):
+        return N32(np.float32.__sub__(self, o))
+
+    def __add__(self, o):
+        return N32(np.float32.__add__(self, o))
+
+    def __mul__(self, o):
+        return N32(np.float32.__mul__(self, o))
+
+    def __pow__(self, o):
+        assert o == 2
+        return N32(np.float32.__mul__(self, self))
+
+
 class _NumpyProxy:
     """Stands in for the name `np` inside the reference's iot_sensors module."""
 
@@ -119,9 +141,19 @@ class _NumpyProxy:
         self.random = _RandomNormalProxy(real.random)
 
     def log10(self, x):
-        if REC.normalise_log10 and isinstance(x, self._real.float32):
+        if REC.normalise and isinstance(x, self._real.float32):
             return self._real.float32(self._real.log10(self._real.float64(x)))
         return self._real.log10(x)
+
+    def array(self, obj, dtype=None, **kw):
+        arr = self._real.array(obj, dtype=dtype, **kw)
+        if REC.normalise and sys._getframe(1).f_code.co_name == "calculate_rssi":
+            return [N32(v) for v in arr]        # only [0] / [1] are read (iot_sensors.py:163-164)
+        return arr
+
+    def sqrt(self, x):
+        r = self._real.sqrt(x)
+        return N32(r) if isinstance(x, N32) else r
 
     def __getattr__(self, name):
         return getattr(self._real, name)

@@ -80,7 +80,7 @@ def default_params(**over):
         penalty_data_loss=-1.0, penalty_starvation=-1000.0,
         penalty_unvisited=-5000.0, penalty_starved=-1000.0,
         starvation_cr_threshold=0.20,
-        normalise_log10=True,
+        normalise=True,
         include_sensor_positions=False,
     )
     p.update(over)
@@ -168,11 +168,16 @@ def _log10_f32(d, normalise):
 def deterministic_rssi(ux, uy, sx, sy, params):
     """iot_sensors.py:161-187 without the shadowing term.  ux,uy,sx,sy float32."""
     alt = params["altitude"]
+    norm = params["normalise"]
     dx = (ux - sx) * 10
     dy = (uy - sy) * 10
-    ground = np.sqrt(dx ** 2 + dy ** 2)
-    d = np.sqrt(ground ** 2 + alt ** 2)
-    lg = _log10_f32(d, params["normalise_log10"])
+    if norm:        # host-independent definitions: x**2 := x*x, log10 correctly rounded
+        ground = np.sqrt(dx * dx + dy * dy)
+        d = np.sqrt(ground * ground + alt ** 2)
+    else:           # numpy's own SIMD `power` / `log10` float32 loops (host dependent)
+        ground = np.sqrt(dx ** 2 + dy ** 2)
+        d = np.sqrt(ground ** 2 + alt ** 2)
+    lg = _log10_f32(d, norm)
     if alt == 100:
         d_break, c_hr = _D_BREAK, _TWO_RAY_HR
     else:

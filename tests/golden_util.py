@@ -38,7 +38,7 @@ class Fixture:
 
     def params(self, **over):
         kw = {_KW[k]: v for k, v in self.meta["env_kwargs"].items()}
-        kw["normalise_log10"] = self.meta["flavour"] == "norm"
+        kw["normalise"] = self.meta["flavour"] == "norm"
         kw.update(over)
         return O.default_params(**kw)
 

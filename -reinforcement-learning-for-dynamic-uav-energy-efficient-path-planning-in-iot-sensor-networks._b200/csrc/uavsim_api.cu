@@ -1,0 +1,606 @@
+// C-ABI layer of libuavsim.so (see include/uavsim.h for the contract and the reference lines each
+// entry point stands in for).  Host logic only: validation, arena layout, parameter conversion,
+// kernel dispatch.  All compute lives in uavsim_kernels.cuh.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "uavsim_launch.cuh"
+#include "uavsim_layout.cuh"
+
+using namespace uavsim;
+
+static_assert(sizeof(uavsim_env_record) == 128, "env record must stay one 128-byte line");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(UAVSIM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr)                                   \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr); \
+    } while (0)
+
+constexpr int64_t kAlign = 256;
+int64_t align_up(int64_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Layout {
+    int64_t rec, sstate, spos, sgen, ssf, stat_sums, error_word, actions, total;
+};
+
+int validate(const uavsim_config* c) {
+    if (!c) return fail(UAVSIM_ERR_INVALID_ARG, "config is NULL");
+    if (c->struct_size != sizeof(uavsim_config))
+        return fail(UAVSIM_ERR_INVALID_ARG, "config.struct_size %u != %zu (ABI mismatch)", c->struct_size,
+                    sizeof(uavsim_config));
+    if (c->num_envs <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "num_envs must be positive");
+    if (c->max_sensors <= 0 || c->max_sensors > UAVSIM_MAX_SENSORS)
+        return fail(UAVSIM_ERR_INVALID_ARG, "max_sensors must be in [1, %d]", UAVSIM_MAX_SENSORS);
+    if (c->num_sensors <= 0 || c->num_sensors > c->max_sensors)
+        return fail(UAVSIM_ERR_INVALID_ARG, "num_sensors must be in [1, max_sensors]");
+    if (c->obs_slots < c->max_sensors || c->obs_slots > UAVSIM_MAX_SENSORS)
+        return fail(UAVSIM_ERR_INVALID_ARG, "obs_slots must be in [max_sensors, %d]", UAVSIM_MAX_SENSORS);
+    if (c->features_per_sensor != 3 && c->features_per_sensor != 5)
+        return fail(UAVSIM_ERR_INVALID_ARG, "features_per_sensor must be 3 or 5 (uav_env.py:349)");
+    if (c->frame_stack != 1) return fail(UAVSIM_ERR_UNSUPPORTED, "frame_stack > 1 is not built yet");
+    if (c->precision != UAVSIM_F64 && c->precision != UAVSIM_F32)
+        return fail(UAVSIM_ERR_INVALID_ARG, "precision must be UAVSIM_F64 or UAVSIM_F32");
+    if (c->rng_mode != UAVSIM_RNG_REPLAY && c->rng_mode != UAVSIM_RNG_PHILOX)
+        return fail(UAVSIM_ERR_INVALID_ARG, "rng_mode must be UAVSIM_RNG_REPLAY or UAVSIM_RNG_PHILOX");
+    if (c->reset_mode != UAVSIM_RESET_FIXED && c->reset_mode != UAVSIM_RESET_DOMAIN_RAND)
+        return fail(UAVSIM_ERR_INVALID_ARG, "reset_mode must be UAVSIM_RESET_FIXED or UAVSIM_RESET_DOMAIN_RAND");
+    if (c->grid_w <= 0 || c->grid_h <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "grid must be positive");
+    if (c->max_steps <= 0 || c->max_steps >= (1 << 24))
+        return fail(UAVSIM_ERR_INVALID_ARG, "max_steps must be in [1, 2^24)");
+    if (!(c->data_generation_rate > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "data_generation_rate must be > 0");
+    if (!(c->max_buffer_size > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "max_buffer_size must be > 0");
+    if (!(c->max_battery > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "max_battery must be > 0");
+    if (!(c->collection_duration > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "collection_duration must be > 0");
+    if (c->init_sf < 7 || c->init_sf > 12) return fail(UAVSIM_ERR_INVALID_ARG, "init_sf must be in [7, 12]");
+    if (c->reset_mode == UAVSIM_RESET_DOMAIN_RAND && c->rng_mode == UAVSIM_RNG_PHILOX) {
+        if (c->num_grids <= 0 || c->num_grids > UAVSIM_MAX_GRIDS)
+            return fail(UAVSIM_ERR_INVALID_ARG, "num_grids must be in [1, %d]", UAVSIM_MAX_GRIDS);
+        for (int i = 0; i < c->num_grids; ++i)
+            if (c->grids[i][0] <= 0 || c->grids[i][1] <= 0)
+                return fail(UAVSIM_ERR_INVALID_ARG, "stage grid %d is not positive", i);
+        if (c->max_start_tries <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "max_start_tries must be positive");
+    }
+    return UAVSIM_OK;
+}
+
+int real_bytes(const uavsim_config* c) { return c->precision == UAVSIM_F64 ? 8 : 4; }
+
+Layout make_layout(const uavsim_config* c) {
+    const int64_t E = c->num_envs, P = c->max_sensors, rb = real_bytes(c);
+    Layout L;
+    int64_t off = 0;
+    L.rec = off;
+    off = align_up(off + E * (int64_t)sizeof(uavsim_env_record));
+    L.sstate = off;
+    off = align_up(off + E * P * 4 * rb);
+    L.spos = off;
+    off = align_up(off + E * P * 8);
+    L.sgen = off;
+    off = align_up(off + E * P * rb);
+    L.ssf = off;
+    off = align_up(off + E * P);
+    L.stat_sums = off;
+    off = align_up(off + UAVSIM_STAT_SUMS * 8);
+    L.error_word = off;
+    off = align_up(off + 8);
+    L.actions = off;
+    off = align_up(off + E * 4);
+    L.total = off;
+    return L;
+}
+
+template <typename Real>
+Params<Real> make_params(const uavsim_config& c) {
+    Params<Real> p;
+    std::memset(&p, 0, sizeof p);
+    p.rate = (Real)c.data_generation_rate;
+    p.maxbuf = (Real)c.max_buffer_size;
+    p.thr = (Real)c.rssi_threshold;
+    p.duty_frac = (Real)(c.duty_cycle / 100.0);  // IoTSensor.duty_cycle_probability, iot_sensors.py:104-106
+    p.cd = (Real)c.collection_duration;
+    p.tx_power = (Real)c.tx_power_dbm;
+    p.noise_floor = (Real)c.noise_floor_dbm;
+    p.lambda = (Real)c.adr_lambda;
+    p.one_minus_lambda = (Real)(1 - c.adr_lambda);
+    p.sigma = (Real)c.shadowing_std_db;
+    p.capture_db = (Real)c.capture_threshold_db;
+    p.c_fspl = (Real)(20 * std::log10(868.0));  // iot_sensors.py:179
+    p.c_ht = (Real)(20 * std::log10(0.5));      // iot_sensors.py:183
+    p.c_hr = (Real)(20 * std::log10(c.altitude_m));
+    p.d_break = (4 * M_PI * 0.5 * c.altitude_m) / 0.345;  // iot_sensors.py:174
+    p.alt2 = (float)((long)c.altitude_m * (long)c.altitude_m);
+    p.d_break_sq = (float)(p.d_break * p.d_break);
+    p.r_per_byte = (Real)c.reward_per_byte;
+    p.r_new = (Real)c.reward_new_sensor;
+    p.r_completion = (Real)c.reward_completion;
+    p.r_urg_red = (Real)c.reward_urgency_reduction;
+    p.r_move = (Real)c.reward_movement;
+    p.p_revisit = (Real)c.penalty_revisit;
+    p.p_boundary = (Real)c.penalty_boundary;
+    p.p_collision = (Real)c.penalty_collision;
+    p.p_battery = (Real)c.penalty_battery;
+    p.p_hover = (Real)c.penalty_hover;
+    p.p_step = (Real)c.penalty_step;
+    p.p_data_loss = (Real)c.penalty_data_loss;
+    p.p_starvation = (Real)c.penalty_starvation;
+    p.p_unvisited = (Real)c.penalty_unvisited;
+    p.p_starved = (Real)c.penalty_starved;
+    p.cr_thr = (Real)c.starvation_cr_threshold;
+    p.prox_eta = (Real)c.prox_eta;
+    p.jain_bonus = (Real)c.jain_bonus;
+    p.max_battery = c.max_battery;
+    p.batt_floor = 0.02 * c.max_battery;                       // uav.py:224
+    p.e_move = (c.power_move_w * 1) / 3600;                    // uav.py:177-178
+    p.e_fail = ((c.power_move_w * 0.5) * 1) / 3600;            // uav.py:125,182-183
+    p.e_hover = (c.power_hover_w * c.collection_duration) / 3600;          // uav.py:205
+    p.used_hover = (c.power_hover_w / (60 * 60)) * c.collection_duration;  // uav.py:263, uav_env.py:530
+    p.min_start_dist = c.min_start_dist;
+    p.max_steps = c.max_steps;
+    p.init_sf = c.init_sf;
+    p.fps = c.features_per_sensor;
+    p.obs_dim = 3 + c.features_per_sensor * c.obs_slots;
+    p.obs_stride = p.obs_dim;
+    p.P = c.max_sensors;
+    p.domain_rand = c.reset_mode == UAVSIM_RESET_DOMAIN_RAND;
+    p.auto_reset = c.auto_reset != 0;
+    p.num_grids = c.num_grids;
+    p.max_start_tries = c.max_start_tries;
+    std::memcpy(p.grids, c.grids, sizeof p.grids);
+    p.key0 = (uint32_t)c.seed;
+    p.key1 = (uint32_t)(c.seed >> 32);
+    p.env_id_offset = c.env_id_offset;
+    return p;
+}
+
+__global__ void init_records_kernel(uavsim_env_record* rec, int E, int W, int H, int N, float sx, float sy,
+                                    double battery, int init_sf, uint8_t* ssf, int P, unsigned long long* error_word) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) *error_word = ~0ull;
+    if (e >= E) return;
+    uavsim_env_record r;
+    memset(&r, 0, sizeof r);
+    r.x = r.start_x = sx;
+    r.y = r.start_y = sy;
+    r.battery = battery;
+    r.grid_w = W;
+    r.grid_h = H;
+    r.num_sensors = N;
+    r.first_full_coverage_step = -1;
+    rec[e] = r;
+    for (int j = 0; j < P; ++j) ssf[(size_t)e * P + j] = (uint8_t)init_sf;
+}
+
+__global__ void scenario_kernel(Buffers b, int P, const float* xy, const int32_t* n, const int32_t* wh, const float* st) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.E) return;
+    uavsim_env_record r = b.rec[e];
+    if (n) r.num_sensors = n[e];
+    if (wh) {
+        r.grid_w = wh[2 * e];
+        r.grid_h = wh[2 * e + 1];
+    }
+    if (st) {
+        r.start_x = st[2 * e];
+        r.start_y = st[2 * e + 1];
+        r.x = r.start_x;
+        r.y = r.start_y;
+    }
+    b.rec[e] = r;
+    if (xy)
+        for (int j = 0; j < P; ++j)
+            b.spos[(size_t)e * P + j] = make_float2(xy[((size_t)e * P + j) * 2], xy[((size_t)e * P + j) * 2 + 1]);
+}
+
+__global__ void check_scenario_kernel(const uavsim_env_record* rec, int E, int P, int* bad) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uavsim_env_record r = rec[e];
+    if (r.num_sensors <= 0 || r.num_sensors > P || r.grid_w <= 0 || r.grid_h <= 0) atomicAdd(bad, 1);
+}
+
+}  // namespace
+
+struct uavsim_handle {
+    uavsim_config cfg;
+    uavsim_dims dims;
+    Layout lay;
+    char* arena = nullptr;
+    bool owns_arena = false;
+    Params<double> p64;
+    Params<float> p32;
+    Buffers buf;
+    bool outputs_bound = false;
+    int64_t launches = 0;
+    int32_t* actions_dev = nullptr;
+};
+
+extern "C" {
+
+int uavsim_abi_version(void) { return UAVSIM_ABI_VERSION; }
+
+const char* uavsim_last_error(void) { return g_err.c_str(); }
+
+int uavsim_default_config(uavsim_config* c) {
+    if (!c) return fail(UAVSIM_ERR_INVALID_ARG, "config is NULL");
+    std::memset(c, 0, sizeof *c);
+    c->struct_size = sizeof *c;
+    c->num_envs = 1;
+    c->max_sensors = 20;
+    c->obs_slots = 20;
+    c->features_per_sensor = 3;
+    c->frame_stack = 1;
+    c->precision = UAVSIM_F32;
+    c->rng_mode = UAVSIM_RNG_PHILOX;
+    c->reset_mode = UAVSIM_RESET_FIXED;
+    c->auto_reset = 1;
+    c->seed = 0;
+    c->env_id_offset = 0;
+    c->grid_w = 500;  // evaluation grid (dqn.py:116-117)
+    c->grid_h = 500;
+    c->num_sensors = 20;
+    c->max_steps = 2100;                   // dqn.py:1069
+    c->data_generation_rate = 22.0 / 10;   // uav_env.py:271
+    c->max_buffer_size = 1000.0;           // uav_env.py:272
+    c->rssi_threshold = -85.0;             // dqn.py:1071
+    c->duty_cycle = 10.0;                  // dqn.py:1072
+    c->max_battery = 274.0;                // dqn.py:1073
+    c->collection_duration = 1.0;          // uav_env.py:279
+    c->start_x = 0.0;                      // uav_env.py:332-333
+    c->start_y = 0.0;
+    c->tx_power_dbm = 14.0;                // iot_sensors.py:46
+    c->noise_floor_dbm = -105.0;           // iot_sensors.py:50
+    c->altitude_m = 100.0;                 // iot_sensors.py:51
+    c->adr_lambda = 0.1;                   // iot_sensors.py:54
+    c->shadowing_std_db = 4.0;             // iot_sensors.py:56
+    c->capture_threshold_db = 6.0;         // uav_env.py:569
+    c->power_move_w = 500.0;               // uav.py:93
+    c->power_hover_w = 700.0;              // uav.py:94
+    c->init_sf = 12;                       // iot_sensors.py:309
+    c->reward_per_byte = 100.0;            // reward_function.py:10-26 with uav_env.py:282-285
+    c->reward_new_sensor = 5000.0;
+    c->reward_completion = 100.0;
+    c->reward_urgency_reduction = 20.0;
+    c->reward_movement = 10.0;
+    c->penalty_revisit = -2.0;
+    c->penalty_boundary = -50.0;
+    c->penalty_collision = -10.0;
+    c->penalty_battery = -0.5;
+    c->penalty_hover = -5.0;
+    c->penalty_step = -0.5;
+    c->penalty_data_loss = -1.0;
+    c->penalty_starvation = -1000.0;
+    c->penalty_unvisited = -5000.0;
+    c->penalty_starved = -1000.0;
+    c->starvation_cr_threshold = 0.20;
+    c->num_grids = 1;                      // curriculum stage 0 (dqn.py:64)
+    c->grids[0][0] = 100;
+    c->grids[0][1] = 100;
+    c->min_start_dist = 50.0;              // dqn.py:127
+    c->max_start_tries = 200;              // dqn.py:128
+    c->prox_eta = 2.0;                     // dqn.py:129
+    c->jain_bonus = 0.5;                   // dqn.py:442
+    return UAVSIM_OK;
+}
+
+int uavsim_query_dims(const uavsim_config* c, uavsim_dims* out) {
+    if (int rc = validate(c)) return rc;
+    if (!out) return fail(UAVSIM_ERR_INVALID_ARG, "out is NULL");
+    std::memset(out, 0, sizeof *out);
+    out->obs_dim = 3 + c->features_per_sensor * c->obs_slots;
+    out->frame_rows = 1;
+    out->obs_row_floats = out->obs_dim * out->frame_rows;
+    out->real_bytes = real_bytes(c);
+    out->arena_bytes = make_layout(c).total;
+    out->replay_step_doubles = (int64_t)UAVSIM_NUM_SLOTS * c->max_sensors;
+    return UAVSIM_OK;
+}
+
+int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, void* stream, uavsim_handle** out) {
+    if (!out) return fail(UAVSIM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (int rc = validate(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    uavsim_handle* h = new (std::nothrow) uavsim_handle();
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "out of host memory");
+    h->cfg = *c;
+    uavsim_query_dims(c, &h->dims);
+    h->lay = make_layout(c);
+    if (arena_dev) {
+        if ((int64_t)arena_bytes < h->lay.total || ((uintptr_t)arena_dev % kAlign) != 0) {
+            delete h;
+            return fail(UAVSIM_ERR_INVALID_ARG, "arena must be >= %lld bytes and %lld-byte aligned",
+                        (long long)h->lay.total, (long long)kAlign);
+        }
+        h->arena = (char*)arena_dev;
+    } else {
+        cudaError_t e = cudaMalloc((void**)&h->arena, (size_t)h->lay.total);
+        if (e != cudaSuccess) {
+            delete h;
+            return cuda_fail(e, "cudaMalloc(arena)");
+        }
+        h->owns_arena = true;
+    }
+    h->p64 = make_params<double>(*c);
+    h->p32 = make_params<float>(*c);
+    Buffers& b = h->buf;
+    std::memset(&b, 0, sizeof b);
+    b.rec = (uavsim_env_record*)(h->arena + h->lay.rec);
+    b.sstate = h->arena + h->lay.sstate;
+    b.spos = (float2*)(h->arena + h->lay.spos);
+    b.sgen = h->arena + h->lay.sgen;
+    b.ssf = (uint8_t*)(h->arena + h->lay.ssf);
+    b.stat_sums = (double*)(h->arena + h->lay.stat_sums);
+    b.error_word = (unsigned long long*)(h->arena + h->lay.error_word);
+    b.E = c->num_envs;
+    h->actions_dev = (int32_t*)(h->arena + h->lay.actions);
+    cudaError_t e = cudaMemsetAsync(h->arena, 0, (size_t)h->lay.total, st);
+    if (e == cudaSuccess) {
+        const int E = c->num_envs;
+        init_records_kernel<<<(E + 255) / 256, 256, 0, st>>>(b.rec, E, c->grid_w, c->grid_h, c->num_sensors,
+                                                            (float)c->start_x, (float)c->start_y, c->max_battery,
+                                                            c->init_sf, b.ssf, c->max_sensors, b.error_word);
+        e = cudaGetLastError();
+        h->launches += 1;
+    }
+    if (e != cudaSuccess) {
+        if (h->owns_arena) cudaFree(h->arena);
+        delete h;
+        return cuda_fail(e, "arena initialisation");
+    }
+    *out = h;
+    return UAVSIM_OK;
+}
+
+int uavsim_destroy(uavsim_handle* h) {
+    if (!h) return UAVSIM_OK;
+    if (h->owns_arena) cudaFree(h->arena);
+    delete h;
+    return UAVSIM_OK;
+}
+
+int uavsim_bind_outputs(uavsim_handle* h, const uavsim_outputs* o, void* stream) {
+    if (!h || !o) return fail(UAVSIM_ERR_INVALID_ARG, "handle/outputs is NULL");
+    if (!o->obs || !o->reward || !o->done) return fail(UAVSIM_ERR_INVALID_ARG, "obs, reward and done are required");
+    Buffers& b = h->buf;
+    b.obs = o->obs;
+    b.reward = o->reward;
+    b.done = o->done;
+    b.terminal_obs = o->terminal_obs;
+    b.episode_stats = o->episode_stats;
+    b.action_mask = o->action_mask;
+    b.step_detail = o->step_detail;
+    b.draw_export = o->draw_export;
+    // ghost sensor slots are written once here and never again (N is fixed per environment)
+    CUDA_TRY(cudaMemsetAsync(b.obs, 0, (size_t)h->cfg.num_envs * h->dims.obs_row_floats * sizeof(float),
+                             (cudaStream_t)stream));
+    h->outputs_bound = true;
+    return UAVSIM_OK;
+}
+
+int uavsim_get_field(uavsim_handle* h, int field, uavsim_field_view* v) {
+    if (!h || !v) return fail(UAVSIM_ERR_INVALID_ARG, "handle/view is NULL");
+    std::memset(v, 0, sizeof *v);
+    const int64_t E = h->cfg.num_envs, P = h->cfg.max_sensors, rb = h->dims.real_bytes;
+    switch (field) {
+        case UAVSIM_FIELD_ENV_RECORD:
+            v->ptr = h->buf.rec;
+            v->elem_bytes = sizeof(uavsim_env_record);
+            v->is_float = 2;
+            v->ndim = 1;
+            v->shape[0] = E;
+            v->stride_bytes[0] = sizeof(uavsim_env_record);
+            break;
+        case UAVSIM_FIELD_SENSOR_STATE:
+            v->ptr = h->buf.sstate;
+            v->elem_bytes = (int32_t)rb;
+            v->is_float = 1;
+            v->ndim = 3;
+            v->shape[0] = E;
+            v->shape[1] = P;
+            v->shape[2] = 4;
+            v->stride_bytes[0] = P * 4 * rb;
+            v->stride_bytes[1] = 4 * rb;
+            v->stride_bytes[2] = rb;
+            break;
+        case UAVSIM_FIELD_SENSOR_POS:
+            v->ptr = h->buf.spos;
+            v->elem_bytes = 4;
+            v->is_float = 1;
+            v->ndim = 3;
+            v->shape[0] = E;
+            v->shape[1] = P;
+            v->shape[2] = 2;
+            v->stride_bytes[0] = P * 8;
+            v->stride_bytes[1] = 8;
+            v->stride_bytes[2] = 4;
+            break;
+        case UAVSIM_FIELD_SENSOR_GEN:
+            v->ptr = h->buf.sgen;
+            v->elem_bytes = (int32_t)rb;
+            v->is_float = 1;
+            v->ndim = 2;
+            v->shape[0] = E;
+            v->shape[1] = P;
+            v->stride_bytes[0] = P * rb;
+            v->stride_bytes[1] = rb;
+            break;
+        case UAVSIM_FIELD_SENSOR_SF:
+            v->ptr = h->buf.ssf;
+            v->elem_bytes = 1;
+            v->is_float = 0;
+            v->ndim = 2;
+            v->shape[0] = E;
+            v->shape[1] = P;
+            v->stride_bytes[0] = P;
+            v->stride_bytes[1] = 1;
+            break;
+        default:
+            return fail(UAVSIM_ERR_INVALID_ARG, "unknown field %d", field);
+    }
+    return UAVSIM_OK;
+}
+
+int uavsim_set_scenario(uavsim_handle* h, const uavsim_scenario* sc, void* stream) {
+    if (!h || !sc) return fail(UAVSIM_ERR_INVALID_ARG, "handle/scenario is NULL");
+    const int E = h->cfg.num_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    scenario_kernel<<<(E + 255) / 256, 256, 0, st>>>(h->buf, h->cfg.max_sensors, sc->sensor_xy, sc->num_sensors,
+                                                     sc->grid_wh, sc->start_xy);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (sc->num_sensors || sc->grid_wh) {  // validated with one sync: scenarios are installed rarely
+        int* bad = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&bad, sizeof(int)));
+        cudaMemsetAsync(bad, 0, sizeof(int), st);
+        check_scenario_kernel<<<(E + 255) / 256, 256, 0, st>>>(h->buf.rec, E, h->cfg.max_sensors, bad);
+        h->launches += 1;
+        int host_bad = 0;
+        cudaError_t e = cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(bad);
+        if (e != cudaSuccess) return cuda_fail(e, "scenario check");
+        if (host_bad)
+            return fail(UAVSIM_ERR_INVALID_ARG, "%d environments have num_sensors outside [1, max_sensors] or a non-positive grid",
+                        host_bad);
+        if (h->outputs_bound)  // N may have changed: re-zero ghost slots
+            CUDA_TRY(cudaMemsetAsync(h->buf.obs, 0, (size_t)E * h->dims.obs_row_floats * sizeof(float), st));
+    }
+    return UAVSIM_OK;
+}
+
+int uavsim_generate_layouts(uavsim_handle* h, void* stream) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    const int E = h->cfg.num_envs;
+    layout_kernel<<<(E + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, (cudaStream_t)stream>>>(
+        h->buf, h->cfg.max_sensors, (uint32_t)h->cfg.seed, (uint32_t)(h->cfg.seed >> 32), h->cfg.env_id_offset);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return UAVSIM_OK;
+}
+
+int uavsim_set_replay(uavsim_handle* h, const uavsim_replay* rp) {
+    if (!h || !rp) return fail(UAVSIM_ERR_INVALID_ARG, "handle/replay is NULL");
+    if (h->cfg.rng_mode != UAVSIM_RNG_REPLAY) return fail(UAVSIM_ERR_STATE, "handle was not created with UAVSIM_RNG_REPLAY");
+    Buffers& b = h->buf;
+    b.step_draws = rp->step_draws;
+    b.reset_draws = rp->reset_draws;
+    b.reset_fill = rp->reset_fill;
+    b.reset_init_sf = rp->reset_init_sf;
+    b.rs_sensor_xy = rp->reset_scenario.sensor_xy;
+    b.rs_num_sensors = rp->reset_scenario.num_sensors;
+    b.rs_grid_wh = rp->reset_scenario.grid_wh;
+    b.rs_start_xy = rp->reset_scenario.start_xy;
+    return UAVSIM_OK;
+}
+
+int uavsim_set_stage_grids(uavsim_handle* h, int32_t n, const int32_t* wh) {
+    if (!h || !wh) return fail(UAVSIM_ERR_INVALID_ARG, "handle/grids is NULL");
+    if (n <= 0 || n > UAVSIM_MAX_GRIDS) return fail(UAVSIM_ERR_INVALID_ARG, "num_grids must be in [1, %d]", UAVSIM_MAX_GRIDS);
+    for (int i = 0; i < n; ++i)
+        if (wh[2 * i] <= 0 || wh[2 * i + 1] <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "stage grid %d is not positive", i);
+    h->cfg.num_grids = n;
+    for (int i = 0; i < n; ++i) {
+        h->cfg.grids[i][0] = wh[2 * i];
+        h->cfg.grids[i][1] = wh[2 * i + 1];
+    }
+    h->p64.num_grids = h->p32.num_grids = n;
+    std::memcpy(h->p64.grids, h->cfg.grids, sizeof h->p64.grids);
+    std::memcpy(h->p32.grids, h->cfg.grids, sizeof h->p32.grids);
+    return UAVSIM_OK;
+}
+
+static int check_ready(uavsim_handle* h, bool reset) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    if (!h->outputs_bound) return fail(UAVSIM_ERR_STATE, "uavsim_bind_outputs has not been called");
+    if (h->cfg.rng_mode == UAVSIM_RNG_REPLAY) {
+        const Buffers& b = h->buf;
+        const bool need_reset_tables = reset || h->cfg.auto_reset;
+        if (!reset && !b.step_draws) return fail(UAVSIM_ERR_STATE, "replay mode: step_draws not set (uavsim_set_replay)");
+        if (need_reset_tables && !b.reset_draws) return fail(UAVSIM_ERR_STATE, "replay mode: reset_draws not set");
+        if (need_reset_tables && h->cfg.reset_mode == UAVSIM_RESET_FIXED && !b.reset_fill)
+            return fail(UAVSIM_ERR_STATE, "replay mode: reset_fill not set");
+    }
+    return UAVSIM_OK;
+}
+
+int uavsim_reset(uavsim_handle* h, const uint8_t* mask, void* stream) {
+    if (int rc = check_ready(h, true)) return rc;
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_reset_f64(h->p64, h->buf, mask, replay, (cudaStream_t)stream)
+                                                   : launch_reset_f32(h->p32, h->buf, mask, replay, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "reset_kernel launch");
+    h->launches += 1;
+    return UAVSIM_OK;
+}
+
+int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
+    if (int rc = check_ready(h, false)) return rc;
+    if (!actions) return fail(UAVSIM_ERR_INVALID_ARG, "actions is NULL");
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    h->buf.step_serial += 1;
+    cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_step_f64(h->p64, h->buf, actions, replay, (cudaStream_t)stream)
+                                                   : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "step_kernel launch");
+    h->launches += 1;
+    return UAVSIM_OK;
+}
+
+int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_host, void* reward_host,
+                     uint8_t* done_host, void* stream) {
+    if (!h || !actions_host || !reward_host || !done_host)
+        return fail(UAVSIM_ERR_INVALID_ARG, "handle/actions/reward/done is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t E = (size_t)h->cfg.num_envs;
+    CUDA_TRY(cudaMemcpyAsync(h->actions_dev, actions_host, E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (int rc = uavsim_step(h, h->actions_dev, stream)) return rc;
+    if (obs_host)
+        CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs, E * h->dims.obs_row_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(reward_host, h->buf.reward, E * h->dims.real_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->buf.done, E, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return UAVSIM_OK;
+}
+
+int uavsim_poll_error(uavsim_handle* h, void* stream, int64_t* first_env) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long w = ~0ull;
+    CUDA_TRY(cudaMemcpyAsync(&w, h->buf.error_word, sizeof w, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (w == ~0ull) return UAVSIM_OK;
+    CUDA_TRY(cudaMemsetAsync(h->buf.error_word, 0xff, sizeof w, st));
+    if (first_env) *first_env = (int64_t)(w & 0xffffffffull);
+    return fail(UAVSIM_ERR_INVALID_ACTION, "Invalid action for env %llu (step call %llu): actions must be in [0, 4]",
+                w & 0xffffffffull, w >> 32);
+}
+
+int uavsim_stat_sums(uavsim_handle* h, double** sums) {
+    if (!h || !sums) return fail(UAVSIM_ERR_INVALID_ARG, "handle/sums is NULL");
+    *sums = h->buf.stat_sums;
+    return UAVSIM_OK;
+}
+
+int64_t uavsim_launch_count(const uavsim_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,14 @@
+// THROUGHPUT build of the step/reset kernels (Real = float): float32 state, MUFU intrinsics,
+// FMA contraction on, shuffle-tree reductions.
+#include "uavsim_launch.cuh"
+
+namespace uavsim {
+cudaError_t launch_step_f32(const Params<float>& p, const Buffers& b, const int32_t* actions, bool replay,
+                            cudaStream_t st) {
+    return launch_step_t<float>(p, b, actions, replay, st);
+}
+cudaError_t launch_reset_f32(const Params<float>& p, const Buffers& b, const uint8_t* mask, bool replay,
+                             cudaStream_t st) {
+    return launch_reset_t<float>(p, b, mask, replay, st);
+}
+}  // namespace uavsim

@@ -1,0 +1,1223 @@
+// Fused batched UAV-LoRa environment step for sm_100a: ONE WARP PER ENVIRONMENT, sensors across
+// lanes (slot j = lane + 32*k, k < SPL), structure-of-arrays state in HBM.
+//
+// What one launch of step_kernel does for every environment (reference file:line under
+// /root/reference/src):
+//   1. age every sensor buffer, cap it, account overflow        environment/iot_sensors.py:114-125
+//   2. MOVE: bounds-checked +-1 cell, battery drain              environment/uav.py:127-185
+//      COLLECT: hover drain (uav.py:187-206), per-sensor EMA-ADR spreading-factor update
+//      (iot_sensors.py:223-259) on a two-ray RSSI (iot_sensors.py:147-197), link-success
+//      sigmoid (iot_sensors.py:202-212), duty-cycle gate, Capture-Effect resolution per SF
+//      group and buffer drain (uav_env.py:518-632, iot_sensors.py:127-145)
+//   3. multi-objective reward                                    rewards/reward_function.py:46-128
+//   4. truncation + terminal penalties                           environment/uav_env.py:471-485
+//   5. observation row (second ADR update + range check)         environment/uav_env.py:638-674
+//   6. DomainRandEnv shaping, padding, episode statistics        agents/dqn/dqn.py:301-444
+//   7. SB3-style in-kernel auto-reset with terminal observation  (DummyVecEnv semantics)
+//
+// The kernel is a template over
+//   Real   : double = PARITY build (float64 accumulators like the reference, reference operation
+//            order, numpy's pairwise summation order, this TU compiled with -fmad=false);
+//            float  = THROUGHPUT build (float32 state, MUFU intrinsics, shuffle reductions).
+//   REPLAY : true  = every random draw is read from a slot-addressed table (parity tests),
+//            false = counter-based Philox4x32-10.
+//   SPL    : sensor slots per lane (1: P <= 32, 2: P <= 64).
+// so the code that is parity-checked bit-for-bit against the oracle is the same source as the code
+// that is benchmarked.  There is no tensor-core work here: the path is elementwise + warp
+// reductions and is bounded by HBM traffic (DESIGN.md has the byte model).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "philox.cuh"
+#include "uavsim.h"
+
+namespace uavsim {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMaxObsDim = 3 + 5 * UAVSIM_MAX_SENSORS;  // 323 floats
+constexpr unsigned kFull = 0xffffffffu;
+
+template <typename Real>
+struct alignas(4 * sizeof(Real)) SensorState {
+    Real buf, tx, lost, ema;  // data_buffer, total_data_transmitted, total_data_lost, avg_rssi (NaN = None)
+};
+
+// Everything the kernels need from uavsim_config, converted once on the host.
+template <typename Real>
+struct Params {
+    // iot_sensors.py / uav_env.py constants
+    Real rate, maxbuf, thr, duty_frac, cd, tx_power, noise_floor, lambda, one_minus_lambda, sigma, capture_db;
+    Real c_fspl, c_ht, c_hr;  // 20*log10(868), 20*log10(0.5), 20*log10(alt)
+    double d_break;           // (4*pi*0.5*alt)/0.345
+    float alt2;               // altitude^2 as the float32 the reference adds (iot_sensors.py:167)
+    float d_break_sq;         // throughput build compares squared distances
+    // RewardFunction
+    Real r_per_byte, r_new, r_completion, r_urg_red, r_move;
+    Real p_revisit, p_boundary, p_collision, p_battery, p_hover, p_step, p_data_loss, p_starvation, p_unvisited,
+        p_starved, cr_thr;
+    Real prox_eta, jain_bonus;
+    // UAV energy (always float64: a handful of per-env scalars)
+    double max_battery, batt_floor, e_move, e_fail, e_hover, used_hover;
+    double min_start_dist;
+    int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
+    int32_t grids[UAVSIM_MAX_GRIDS][2];
+    uint32_t key0, key1;
+    int64_t env_id_offset;
+};
+
+struct Buffers {
+    // state (arena)
+    uavsim_env_record* rec;
+    void* sstate;  // SensorState<Real>[E][P]
+    float2* spos;  // [E][P]
+    void* sgen;    // Real[E][P]
+    uint8_t* ssf;  // [E][P]
+    // outputs
+    float* obs;
+    void* reward;
+    uint8_t* done;
+    float* terminal_obs;
+    double* episode_stats;
+    uint8_t* action_mask;
+    double* step_detail;
+    void* draw_export;
+    // replay
+    const double* step_draws;
+    const double* reset_draws;
+    const double* reset_fill;
+    const int32_t* reset_init_sf;
+    const float* rs_sensor_xy;
+    const int32_t* rs_num_sensors;
+    const int32_t* rs_grid_wh;
+    const float* rs_start_xy;
+    // bookkeeping
+    double* stat_sums;
+    unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
+    int32_t E;
+    uint32_t step_serial;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T shfl(T v, int src) {
+    return __shfl_sync(kFull, v, src);
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        T u = __shfl_xor_sync(kFull, v, o);
+        v = u > v ? u : v;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        T u = __shfl_xor_sync(kFull, v, o);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+
+// numpy's pairwise summation for n <= 128 (numpy/_core/src/umath/loops_utils.h.src): what np.sum /
+// np.mean / np.var do on the reference's small arrays.  Uniform across the warp (reads shared memory).
+template <typename T>
+__device__ __forceinline__ T np_pairwise(const T* a, int n) {
+    if (n < 8) {
+        T r = T(0);
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    T r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += a[i + 0];
+        r1 += a[i + 1];
+        r2 += a[i + 2];
+        r3 += a[i + 3];
+        r4 += a[i + 4];
+        r5 += a[i + 5];
+        r6 += a[i + 6];
+        r7 += a[i + 7];
+    }
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+enum SumOrder { kSumNumpy, kSumSequential };
+
+// Sum of one value per sensor slot over the N real sensors of this warp's environment.
+//   parity build   : staged through shared memory and added in the reference's order
+//                    (numpy pairwise, or left-to-right for Python loops) -> bit-identical floats
+//   throughput build: lane-local add + xor-shuffle tree
+template <typename Real, int SPL, typename T>
+__device__ __forceinline__ T sensor_sum(const T (&v)[SPL], int N, int lane, double* scratch, SumOrder order) {
+    if constexpr (std::is_same<Real, double>::value) {
+        T* s = reinterpret_cast<T*>(scratch);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int j = lane + 32 * k;
+            if (j < N) s[j] = v[k];
+        }
+        __syncwarp();
+        T r;
+        if (order == kSumNumpy) {
+            r = np_pairwise(s, N);
+        } else {
+            r = T(0);
+            for (int i = 0; i < N; ++i) r += s[i];
+        }
+        __syncwarp();
+        return r;
+    } else {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) acc += (lane + 32 * k < N) ? v[k] : T(0);
+        return warp_sum(acc);
+    }
+}
+
+__device__ __forceinline__ double data_rate_of(int sf) {  // iot_sensors.py:13-20
+    switch (sf) {
+        case 7: return 5470 / 8.0;
+        case 8: return 3125 / 8.0;
+        case 9: return 1760 / 8.0;
+        case 10: return 980 / 8.0;
+        case 11: return 440 / 8.0;
+        default: return 250 / 8.0;
+    }
+}
+__device__ __forceinline__ double required_snr_of(int sf) {  // iot_sensors.py:22-29 (:199-200 default)
+    switch (sf) {
+        case 7: return -6.0;
+        case 8: return -9.0;
+        case 9: return -12.0;
+        case 10: return -15.0;
+        case 11: return -17.5;
+        case 12: return -20.0;
+        default: return 7.5;
+    }
+}
+__device__ __forceinline__ float link_quality_of(int sf) {  // uav_env.py:647
+    switch (sf) {
+        case 7: return 1.0f;
+        case 8: return 0.8f;
+        case 9: return 0.6f;
+        case 10: return 0.4f;
+        case 11: return 0.2f;
+        default: return 0.1f;
+    }
+}
+
+// Deterministic part of IoTSensor.calculate_rssi (iot_sensors.py:161-187).  Evaluated ONCE per
+// sensor per step: the UAV does not move between the up-to-five draws a step makes on a sensor.
+template <typename Real>
+__device__ __forceinline__ Real det_rssi(const Params<Real>& p, float ux, float uy, float sx, float sy) {
+    const float dx = (ux - sx) * 10.0f;
+    const float dy = (uy - sy) * 10.0f;
+    if constexpr (std::is_same<Real, double>::value) {
+        // reference op order in float32 (this TU is built with -fmad=false, so no contraction)
+        const float g = sqrtf(dx * dx + dy * dy);
+        const float d = sqrtf(g * g + p.alt2);
+        const float lg = (float)log10((double)d);  // correctly rounded float32 log10 (normalised definition)
+        double pl;
+        if ((double)d < p.d_break) {
+            const float t = 20.0f * lg;
+            pl = ((double)t + p.c_fspl) - 28;
+        } else {
+            const float t = 40.0f * lg;
+            pl = ((double)t - p.c_ht) - p.c_hr;
+        }
+        return p.tx_power - pl;
+    } else {
+        // log10(d) = 0.5*log10(d^2): one MUFU.LG2, no square roots
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, p.alt2));
+        const float l2 = __log2f(d2);
+        const float k = 0.30102999566398120f * 0.5f;  // log10(2)/2
+        return d2 < p.d_break_sq ? fmaf(-20.0f * k, l2, p.tx_power - p.c_fspl + 28.0f)
+                                 : fmaf(-40.0f * k, l2, p.tx_power + p.c_ht + p.c_hr);
+    }
+}
+
+// IoTSensor.update_spreading_factor (iot_sensors.py:223-259).  "No threshold matched" keeps the SF.
+template <typename Real>
+__device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Real& ema, int& sf) {
+    if (ema != ema)
+        ema = rssi;
+    else
+        ema = (p.lambda * rssi) + (p.one_minus_lambda * ema);
+    if (ema > Real(-60))
+        sf = 7;
+    else if (ema > Real(-70))
+        sf = 9;
+    else if (ema > Real(-78))
+        sf = 11;
+    else if (ema > Real(-85))
+        sf = 12;
+}
+
+// UAVEnvironment._calculate_urgency (uav_env.py:376-384)
+template <typename Real>
+__device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real lost, Real gen) {
+    const Real util = buf / p.maxbuf;
+    const Real lr = gen > Real(0) ? lost / gen : Real(0);
+    const Real u = util * (Real(1) + lr * Real(10));
+    return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// draws
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, Real sigma, Real& z0, Real& z1) {
+    if constexpr (std::is_same<Real, double>::value) {
+        const double u1 = ((double)a + 0.5) * 2.3283064365386963e-10;  // (0,1)
+        const double u2 = ((double)b + 0.5) * 2.3283064365386963e-10;
+        const double r = sigma * sqrt(-2.0 * log(u1));
+        double s, c;
+        sincospi(2.0 * u2, &s, &c);
+        z0 = r * c;
+        z1 = r * s;
+    } else {
+        const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
+        const float u2 = (float)b * 2.3283064365386963e-10f;
+        const float r = sigma * sqrtf(-1.3862943611198906f * __log2f(u1));  // -2 ln u = -2 ln2 lg2 u
+        float s, c;
+        __sincosf(6.2831853071795865f * u2, &s, &c);
+        z0 = r * c;
+        z1 = r * s;
+    }
+}
+
+template <typename Real>
+__device__ __forceinline__ Real u01(uint32_t a) {
+    if constexpr (std::is_same<Real, double>::value)
+        return ((double)a + 0.5) * 2.3283064365386963e-10;
+    else
+        return fminf(fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
+}
+
+template <typename Real, bool REPLAY>
+struct Draws {
+    const double* tab;  // replay: this env's [6][P] table
+    Real* exp;          // optional export of the draws actually used, [6][P]
+    int P;
+    uint32_t k0, k1, env_lo, env_hi, episode, step;
+    Real sigma;
+
+    __device__ __forceinline__ void put(int slot, int j, Real v) const {
+        if (exp) exp[slot * P + j] = v;
+    }
+    __device__ __forceinline__ Philox4 call(uint32_t stream, int j, int c) const {
+        return philox4x32_10(env_lo, env_hi | (stream << 24), episode, (step << 7) | ((uint32_t)j << 1) | (uint32_t)c, k0,
+                             k1);
+    }
+    // observation draws D (ADR) and E (range check): uav_env.py:654-660
+    __device__ __forceinline__ void obs_pair(int j, Real& d, Real& e) const {
+        if constexpr (REPLAY) {
+            d = (Real)tab[UAVSIM_SLOT_D * P + j];
+            e = (Real)tab[UAVSIM_SLOT_E * P + j];
+        } else {
+            const Philox4 r = call(kStreamStep, j, 0);
+            box_muller<Real>(r.x, r.y, sigma, d, e);
+            put(UAVSIM_SLOT_D, j, d);
+            put(UAVSIM_SLOT_E, j, e);
+        }
+    }
+    // collect-step draws A (ADR), B (link probability), U (duty-cycle uniform): uav_env.py:535-551
+    __device__ __forceinline__ void collect_triple(int j, Real& a, Real& b, Real& u) const {
+        if constexpr (REPLAY) {
+            a = (Real)tab[UAVSIM_SLOT_A * P + j];
+            b = (Real)tab[UAVSIM_SLOT_B * P + j];
+            u = (Real)tab[UAVSIM_SLOT_U * P + j];
+        } else {
+            const Philox4 r = call(kStreamStep, j, 0);
+            box_muller<Real>(r.z, r.w, sigma, a, b);
+            const Philox4 q = call(kStreamStep, j, 1);
+            u = u01<Real>(q.x);
+            put(UAVSIM_SLOT_A, j, a);
+            put(UAVSIM_SLOT_B, j, b);
+            put(UAVSIM_SLOT_U, j, u);
+        }
+    }
+    // winner's range-check draw C: iot_sensors.py:131-133 via uav_env.py:581
+    __device__ __forceinline__ Real winner_draw(int j) const {
+        if constexpr (REPLAY) {
+            return (Real)tab[UAVSIM_SLOT_C * P + j];
+        } else {
+            const Philox4 q = call(kStreamStep, j, 1);
+            Real c, unused;
+            box_muller<Real>(q.y, q.z, sigma, c, unused);
+            put(UAVSIM_SLOT_C, j, c);
+            return c;
+        }
+    }
+    __device__ __forceinline__ void clear_export(int lane) const {
+        if (exp) {
+            const Real nan = Real(CUDART_NAN);
+            for (int i = lane; i < UAVSIM_NUM_SLOTS * P; i += 32) exp[i] = nan;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-lane sensor registers
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+struct Sensor {
+    Real buf, tx, lost, ema, gen;  // gen: parity = total_data_generated; throughput = value at reset
+    Real det, cur;                 // deterministic RSSI here; current_rssi of draw A
+    float sx, sy;
+    int sf;
+    bool active, attempt;
+};
+
+template <typename Real>
+__device__ __forceinline__ Real generated_of(const Params<Real>& p, const Sensor<Real>& s, float elapsed) {
+    if constexpr (std::is_same<Real, double>::value)
+        return s.gen;
+    else
+        return fmaf(p.rate, elapsed, s.gen);  // total_data_generated = at_reset + rate * sum(dt)
+}
+
+struct Scratch {
+    float obs[kMaxObsDim + 1];
+    double red[UAVSIM_MAX_SENSORS];
+};
+
+template <typename Real, int SPL>
+__device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real>& p, int e, int N, int lane,
+                                             Sensor<Real> (&s)[SPL]) {
+    const size_t row = (size_t)e * p.P;
+    const SensorState<Real>* st = reinterpret_cast<const SensorState<Real>*>(b.sstate) + row;
+    const Real* gen = reinterpret_cast<const Real*>(b.sgen) + row;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        s[k].active = j < N;
+        s[k].attempt = false;
+        s[k].det = Real(0);
+        s[k].cur = Real(0);
+        if (s[k].active) {
+            const SensorState<Real> v = st[j];
+            const float2 xy = b.spos[row + j];
+            s[k].buf = v.buf;
+            s[k].tx = v.tx;
+            s[k].lost = v.lost;
+            s[k].ema = v.ema;
+            s[k].gen = gen[j];
+            s[k].sx = xy.x;
+            s[k].sy = xy.y;
+            s[k].sf = b.ssf[row + j];
+        } else {
+            s[k].buf = s[k].tx = s[k].lost = s[k].gen = Real(0);
+            s[k].ema = Real(CUDART_NAN);
+            s[k].sx = s[k].sy = 0.f;
+            s[k].sf = 12;
+        }
+    }
+}
+
+template <typename Real, int SPL>
+__device__ __forceinline__ void store_sensors(const Buffers& b, const Params<Real>& p, int e, int lane,
+                                              const Sensor<Real> (&s)[SPL], bool write_static) {
+    const size_t row = (size_t)e * p.P;
+    SensorState<Real>* st = reinterpret_cast<SensorState<Real>*>(b.sstate) + row;
+    Real* gen = reinterpret_cast<Real*>(b.sgen) + row;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        if (s[k].active) {
+            SensorState<Real> v;
+            v.buf = s[k].buf;
+            v.tx = s[k].tx;
+            v.lost = s[k].lost;
+            v.ema = s[k].ema;
+            st[j] = v;
+            b.ssf[row + j] = (uint8_t)s[k].sf;
+            // parity build accumulates total_data_generated; throughput build only rewrites it on reset
+            if (std::is_same<Real, double>::value || write_static) gen[j] = s[k].gen;
+            if (write_static) b.spos[row + j] = make_float2(s[k].sx, s[k].sy);
+        }
+    }
+}
+
+__device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H) {  // derived: uav.py:175
+    const float fw = (float)W, fh = (float)H;
+    uint8_t m = 1u << 4;
+    const bool xin = (0.f <= x) && (x < fw), yin = (0.f <= y) && (y < fh);
+    if (xin && 0.f <= y + 1.0f && y + 1.0f < fh) m |= 1u << 0;
+    if (xin && 0.f <= y - 1.0f && y - 1.0f < fh) m |= 1u << 1;
+    if (yin && 0.f <= x - 1.0f && x - 1.0f < fw) m |= 1u << 2;
+    if (yin && 0.f <= x + 1.0f && x + 1.0f < fw) m |= 1u << 3;
+    return m;
+}
+
+// UAVEnvironment._get_observation (uav_env.py:638-674) + zero padding to obs_slots (dqn.py:286-298).
+// Mutates EMA / SF (draw D) and draws E.  The row is staged in shared memory and written with
+// consecutive lanes on consecutive floats; ghost slots are zero-filled once when the buffer is
+// bound and never touched again (N is fixed per environment).
+template <typename Real, bool REPLAY, int SPL>
+__device__ __forceinline__ void observe(const Params<Real>& p, const uavsim_env_record& r, Sensor<Real> (&s)[SPL],
+                                        const Draws<Real, REPLAY>& dr, int lane, float* stage, float* out) {
+    const int N = r.num_sensors;
+    __syncwarp();
+    if (lane == 0) {
+        if constexpr (std::is_same<Real, double>::value) {
+            stage[0] = (float)((double)r.x / (double)r.grid_w);
+            stage[1] = (float)((double)r.y / (double)r.grid_h);
+            stage[2] = (float)(r.battery / p.max_battery);
+        } else {
+            stage[0] = r.x / (float)r.grid_w;
+            stage[1] = r.y / (float)r.grid_h;
+            stage[2] = (float)r.battery / (float)p.max_battery;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        if (s[k].active) {
+            const Real urg = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], r.elapsed_s));
+            Real d, e;
+            dr.obs_pair(j, d, e);
+            adr_update(p, s[k].det + d, s[k].ema, s[k].sf);
+            const bool in_range = (s[k].det + e) >= p.thr;
+            float* o = stage + 3 + p.fps * j;
+            o[0] = (float)(s[k].buf / p.maxbuf);
+            o[1] = (float)urg;
+            o[2] = in_range ? link_quality_of(s[k].sf) : 0.0f;
+            if (p.fps == 5) {  // include_sensor_positions, uav_env.py:668-672
+                if constexpr (std::is_same<Real, double>::value) {
+                    o[3] = (float)(((double)s[k].sx - (double)r.x) / (double)r.grid_w);
+                    o[4] = (float)(((double)s[k].sy - (double)r.y) / (double)r.grid_h);
+                } else {
+                    o[3] = (s[k].sx - r.x) / (float)r.grid_w;
+                    o[4] = (s[k].sy - r.y) / (float)r.grid_h;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int n = 3 + p.fps * N;
+    for (int i = lane; i < n; i += 32) out[i] = stage[i];
+    __syncwarp();
+}
+
+// DomainRandEnv._dist_to_nearest_with_data (dqn.py:405-412): float32 norm, min over sensors with data.
+template <typename Real, int SPL>
+__device__ __forceinline__ float nearest_with_data(const uavsim_env_record& r, const Sensor<Real> (&s)[SPL]) {
+    float best = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        if (s[k].active && s[k].buf > Real(0)) {
+            const float dx = s[k].sx - r.x, dy = s[k].sy - r.y;
+            best = fminf(best, sqrtf(dx * dx + dy * dy));
+        }
+    }
+    best = warp_min(best);
+    return best == CUDART_INF_F ? 0.0f : best;
+}
+
+template <typename Real, int SPL>
+__device__ __forceinline__ void compute_det(const Params<Real>& p, const uavsim_env_record& r, Sensor<Real> (&s)[SPL]) {
+#pragma unroll
+    for (int k = 0; k < SPL; ++k)
+        if (s[k].active) s[k].det = det_rssi(p, r.x, r.y, s[k].sx, s[k].sy);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset
+// ------------------------------------------------------------------------------------------------
+// Episode statistics written when an environment finishes: DomainRandEnv.last_episode_stats
+// (dqn.py:305-331) + what Monitor reports.  Rare path: plain float64 shuffle reductions.
+template <typename Real, int SPL>
+__device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const Buffers& b, int e, int lane,
+                                                    const uavsim_env_record& r, const Sensor<Real> (&s)[SPL]) {
+    double g = 0, t = 0, l = 0, s1 = 0, s2 = 0, cnt = 0;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        if (s[k].active) {
+            const double gen = (double)generated_of(p, s[k], r.elapsed_s);
+            g += gen;
+            t += (double)s[k].tx;
+            l += (double)s[k].lost;
+            if (gen > 0) {
+                const double rate = (double)s[k].tx / gen * 100;
+                s1 += rate;
+                s2 += rate * rate;
+                cnt += 1;
+            }
+        }
+    }
+    g = warp_sum(g);
+    t = warp_sum(t);
+    l = warp_sum(l);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+        const int N = r.num_sensors;
+        const int nv = __popc(r.visited_lo) + __popc(r.visited_hi);
+        const double used = p.max_battery - r.battery;
+        const double mean = cnt > 0 ? s1 / cnt : 0.0;
+        const double var = cnt > 0 ? fmax(s2 / cnt - mean * mean, 0.0) : 0.0;
+        double v[UAVSIM_STAT_COUNT];
+        v[UAVSIM_STAT_RETURN] = r.episode_return;
+        v[UAVSIM_STAT_LENGTH] = r.step;
+        v[UAVSIM_STAT_TOTAL_GENERATED] = g;
+        v[UAVSIM_STAT_TOTAL_COLLECTED] = t;
+        v[UAVSIM_STAT_TOTAL_LOST] = l;
+        v[UAVSIM_STAT_BATTERY_REMAINING] = r.battery;
+        v[UAVSIM_STAT_NDR] = (double)nv / N * 100;
+        v[UAVSIM_STAT_FAIRNESS_STD] = sqrt(var);
+        v[UAVSIM_STAT_JAINS] = (cnt > 0 && s2 > 0) ? (s1 * s1) / (cnt * s2) : 1.0;  // dqn.py:446-451
+        v[UAVSIM_STAT_GRID_W] = r.grid_w;
+        v[UAVSIM_STAT_GRID_H] = r.grid_h;
+        v[UAVSIM_STAT_NUM_SENSORS] = N;
+        v[UAVSIM_STAT_DATA_EFFICIENCY] = g > 0 ? t / g * 100 : 0.0;
+        v[UAVSIM_STAT_BYTES_PER_WH] = used > 0 ? t / used : 0.0;
+        v[UAVSIM_STAT_TIME_TO_COVERAGE] = r.first_full_coverage_step;
+        v[UAVSIM_STAT_CAPTURE_TRIGGERS] = r.capture_triggers;
+        v[UAVSIM_STAT_BOUNDARY_HITS] = r.boundary_hits;
+        v[UAVSIM_STAT_EDGE_STEPS] = r.edge_steps;
+        v[UAVSIM_STAT_COLLISIONS] = r.collisions;
+        v[UAVSIM_STAT_BASE_RETURN] = r.total_reward;
+        if (b.episode_stats)
+            for (int i = 0; i < UAVSIM_STAT_COUNT; ++i) b.episode_stats[(size_t)e * UAVSIM_STAT_COUNT + i] = v[i];
+        if (b.stat_sums) {
+            for (int i = 0; i < UAVSIM_STAT_COUNT; ++i) atomicAdd(b.stat_sums + i, v[i]);
+            atomicAdd(b.stat_sums + UAVSIM_STAT_COUNT, 1.0);
+        }
+    }
+}
+
+// Start a new episode for this warp's environment (state in registers), then write its first
+// observation.  FIXED: UAVEnvironment.reset (uav_env.py:400-427, iot_sensors.py:305-321).
+// DOMAIN_RAND: DomainRandEnv.reset (dqn.py:301-372).  `r.episode` already names the NEW episode.
+template <typename Real, bool REPLAY, int SPL>
+__device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& b, int e, int lane, uavsim_env_record& r,
+                                          Sensor<Real> (&s)[SPL], Scratch& sc, bool& layout_changed, Real* exp) {
+    const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+    const uint32_t env_lo = (uint32_t)gid, env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
+    int init_sf = p.init_sf;
+    layout_changed = false;
+
+    if (p.domain_rand) {
+        layout_changed = true;
+        if constexpr (REPLAY) {
+            // injected scenario (the reference draws it from unseeded / global generators)
+            if (b.reset_init_sf) init_sf = b.reset_init_sf[e];
+            if (b.rs_grid_wh) {
+                r.grid_w = b.rs_grid_wh[2 * e];
+                r.grid_h = b.rs_grid_wh[2 * e + 1];
+            }
+            if (b.rs_num_sensors) r.num_sensors = b.rs_num_sensors[e];
+            if (b.rs_start_xy) {
+                r.start_x = b.rs_start_xy[2 * e];
+                r.start_y = b.rs_start_xy[2 * e + 1];
+            }
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                s[k].active = j < r.num_sensors;
+                if (s[k].active && b.rs_sensor_xy) {
+                    s[k].sx = b.rs_sensor_xy[((size_t)e * p.P + j) * 2];
+                    s[k].sy = b.rs_sensor_xy[((size_t)e * p.P + j) * 2 + 1];
+                }
+            }
+        } else {
+            // (a) SF inherited from the OLD sensor 0 after the parent reset's observation pass at the
+            //     OLD start position (dqn.py:338-353 with uav_env.py:407-427): one ADR update from None.
+            {
+                const float s0x = shfl(s[0].sx, 0), s0y = shfl(s[0].sy, 0);
+                const Real det0 = det_rssi(p, r.start_x, r.start_y, s0x, s0y);
+                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), r.episode, 1, p.key0, p.key1);
+                Real z0, z1;
+                box_muller<Real>(q.x, q.y, p.sigma, z0, z1);
+                Real ema = Real(CUDART_NAN);
+                int sf = p.init_sf;
+                adr_update(p, det0 + z0, ema, sf);
+                init_sf = sf;
+                // (b) grid from the current curriculum stage (dqn.py:280-283)
+                const Philox4 g = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), r.episode, 0, p.key0, p.key1);
+                const int gi = (int)(g.x % (uint32_t)p.num_grids);
+                r.grid_w = p.grids[gi][0];
+                r.grid_h = p.grids[gi][1];
+            }
+            // (c) uniform layout (dqn.py:342-343, _layout_uniform :135-137)
+            const double W = (double)r.grid_w, H = (double)r.grid_h;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                s[k].active = j < r.num_sensors;
+                if (s[k].active) {
+                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamLayout << 24), r.episode, (uint32_t)j, p.key0,
+                                                    p.key1);
+                    s[k].sx = (float)(u01<double>(q.x) * W);
+                    s[k].sy = (float)(u01<double>(q.y) * H);
+                }
+            }
+            // (d) far start: first candidate >= min_start_dist from every sensor, else the furthest of
+            //     max_start_tries (dqn.py:375-403).  32 candidates per round, one per lane.
+            float2* pos = reinterpret_cast<float2*>(sc.red);  // 64 float2 = 512 B
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < SPL; ++k)
+                if (s[k].active) pos[lane + 32 * k] = make_float2(s[k].sx, s[k].sy);
+            __syncwarp();
+            float best_d = -1.0f, best_x = 0.f, best_y = 0.f;
+            bool found = false;
+            for (int base = 0; base < p.max_start_tries && !found; base += 32) {
+                const int t = base + lane;
+                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamStart << 24), r.episode, (uint32_t)t, p.key0, p.key1);
+                const float cx = (float)(0.05 * W + (0.95 * W - 0.05 * W) * u01<double>(q.x));
+                const float cy = (float)(0.05 * H + (0.95 * H - 0.05 * H) * u01<double>(q.y));
+                float dmin = CUDART_INF_F;
+                for (int i = 0; i < r.num_sensors; ++i) {
+                    const float dx = cx - pos[i].x, dy = cy - pos[i].y;
+                    dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
+                }
+                const bool valid = t < p.max_start_tries;
+                const unsigned ok = __ballot_sync(kFull, valid && (double)dmin >= p.min_start_dist);
+                if (ok) {
+                    const int src = __ffs(ok) - 1;
+                    best_x = shfl(cx, src);
+                    best_y = shfl(cy, src);
+                    found = true;
+                } else {
+                    // running "furthest so far", first occurrence wins ties (strict > at dqn.py:397)
+                    float d = valid ? dmin : -2.0f;
+                    const float m = warp_max(d);
+                    if (m > best_d) {
+                        const unsigned who = __ballot_sync(kFull, d == m);
+                        const int src = __ffs(who) - 1;
+                        best_d = m;
+                        best_x = shfl(cx, src);
+                        best_y = shfl(cy, src);
+                    }
+                }
+            }
+            __syncwarp();
+            r.start_x = best_x;
+            r.start_y = best_y;
+        }
+    }
+
+    // UAV.reset (uav.py:241-258) and the episode counters (uav_env.py:412-424)
+    r.x = r.start_x;
+    r.y = r.start_y;
+    r.battery = p.max_battery;
+    r.total_reward = 0.0;
+    r.total_data_collected = 0.0;
+    r.episode_return = 0.0;
+    r.last_step_bytes = 0.f;
+    r.elapsed_s = 0.f;
+    r.step = 0;
+    r.visited_lo = r.visited_hi = 0u;
+    r.capture_triggers = r.boundary_hits = r.edge_steps = r.collisions = r.delivered = 0;
+    r.first_full_coverage_step = -1;
+
+    // IoTSensor.reset (iot_sensors.py:305-321) / fresh IoTSensor objects (dqn.py:345-360)
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        s[k].active = j < r.num_sensors;
+        if (s[k].active) {
+            if (p.domain_rand) {
+                s[k].buf = Real(0);
+            } else {
+                Real fill;
+                if constexpr (REPLAY) {
+                    fill = (Real)b.reset_fill[(size_t)e * p.P + j];
+                } else {
+                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamFill << 24), r.episode, (uint32_t)j, p.key0,
+                                                    p.key1);
+                    fill = Real(0.20) + (Real(0.60) - Real(0.20)) * u01<Real>(q.x);  // np_random.uniform(0.20, 0.60)
+                }
+                fill = fill < Real(0) ? Real(0) : (fill > Real(1) ? Real(1) : fill);
+                s[k].buf = p.maxbuf * fill;
+            }
+            s[k].gen = s[k].buf;
+            s[k].tx = Real(0);
+            s[k].lost = Real(0);
+            s[k].ema = Real(CUDART_NAN);
+            s[k].sf = init_sf;
+            if (exp) exp[UAVSIM_SLOT_U * p.P + j] = s[k].buf / p.maxbuf;  // the fill actually used (diagnostic)
+        }
+    }
+    r.reserved[0] = init_sf;
+    compute_det(p, r, s);
+    Draws<Real, REPLAY> dr;
+    dr.P = p.P;
+    dr.sigma = p.sigma;
+    dr.k0 = p.key0;
+    dr.k1 = p.key1;
+    dr.env_lo = env_lo;
+    dr.env_hi = env_hi;
+    dr.episode = r.episode;
+    dr.step = 0;
+    dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+    dr.exp = exp;
+    float* out = b.obs + (size_t)e * p.obs_stride;
+    observe<Real, REPLAY, SPL>(p, r, s, dr, lane, sc.obs, out);
+    for (int i = 3 + p.fps * r.num_sensors + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
+    r.prev_dist_nearest = p.domain_rand ? nearest_with_data(r, s) : 0.f;
+    if (b.action_mask && lane == 0) b.action_mask[e] = action_mask_of(r.x, r.y, r.grid_w, r.grid_h);
+}
+
+template <typename Real, bool REPLAY, int SPL>
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ Params<Real> p,
+                                                         const __grid_constant__ Buffers b, const uint8_t* mask) {
+    __shared__ Scratch scratch[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= b.E) return;
+    if (mask && !mask[e]) return;
+    uavsim_env_record r = b.rec[e];
+    Sensor<Real> s[SPL];
+    load_sensors<Real, SPL>(b, p, e, r.num_sensors, lane, s);
+    bool layout_changed;
+    Real* exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+    if (exp) {
+        const Real nan = Real(CUDART_NAN);
+        for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
+        __syncwarp();
+    }
+    reset_env<Real, REPLAY, SPL>(p, b, e, lane, r, s, scratch[warp], layout_changed, exp);
+    r.episode += 1;  // the next reset (in-step or explicit) starts a new counter block
+    store_sensors<Real, SPL>(b, p, e, lane, s, true);
+    if (lane == 0) {
+        b.rec[e] = r;
+        if (b.done) b.done[e] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------
+// (value, index) arg-max over the lanes of one SF group; ties -> lowest sensor index, which is what
+// Python's stable sorted(..., reverse=True) yields (uav_env.py:564-566).
+template <typename Real>
+__device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& imax) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const Real ov = __shfl_xor_sync(kFull, v, o);
+        const int oi = __shfl_xor_sync(kFull, idx, o);
+        if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) {
+            v = ov;
+            idx = oi;
+        }
+    }
+    vmax = v;
+    imax = idx;
+}
+
+template <typename Real, bool REPLAY, int SPL>
+__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ Params<Real> p,
+                                                        const __grid_constant__ Buffers b, const int32_t* __restrict__ actions) {
+    __shared__ Scratch scratch[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= b.E) return;
+    Scratch& sc = scratch[warp];
+    constexpr bool kParity = std::is_same<Real, double>::value;
+
+    const int action = actions[e];
+    if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
+        if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+        return;
+    }
+    uavsim_env_record r = b.rec[e];
+    const int N = r.num_sensors;
+    Sensor<Real> s[SPL];
+    load_sensors<Real, SPL>(b, p, e, N, lane, s);
+
+    const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+    Draws<Real, REPLAY> dr;
+    dr.P = p.P;
+    dr.sigma = p.sigma;
+    dr.k0 = p.key0;
+    dr.k1 = p.key1;
+    dr.env_lo = (uint32_t)gid;
+    dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
+    dr.episode = r.episode - 1;  // r.episode counts resets done; the running episode is one less
+    dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+    dr.exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+    if (!REPLAY) dr.clear_export(lane);
+
+    const float prev_dist = r.prev_dist_nearest;
+
+    // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
+    r.step += 1;
+    dr.step = (uint32_t)r.step;
+    {
+        const double W = r.grid_w, H = r.grid_h, ux = r.x, uy = r.y, eps = 1e-6;
+        if (ux <= eps || uy <= eps || ux >= W - 1 - eps || uy >= H - 1 - eps) r.edge_steps += 1;
+    }
+    const bool collect = action == 4;
+    const Real dt = collect ? p.cd : Real(1);
+    r.elapsed_s += (float)dt;
+
+    // ---- iot_sensors.py:114-125: age the buffers ----
+    Real loss[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        loss[k] = Real(0);
+        if (s[k].active) {
+            const Real nw = p.rate * dt;
+            if constexpr (kParity) s[k].gen += nw;
+            const Real pot = s[k].buf + nw;
+            if (pot > p.maxbuf) {
+                loss[k] = pot - p.maxbuf;
+                s[k].buf = p.maxbuf;
+                s[k].lost += loss[k];
+            } else {
+                s[k].buf = pot;
+            }
+        }
+    }
+    const Real step_loss = sensor_sum<Real, SPL>(loss, N, lane, sc.red, kSumSequential);
+
+    Real reward;
+    int collisions = 0;
+    Real total_bytes = Real(0), urg_red = Real(0), mean_urg = Real(0);
+    bool any_new = false, was_empty = false, all_collected = false;
+    unsigned long long att_mask = 0ull, win_mask = 0ull;
+
+    if (!collect) {
+        // ---- uav.py:127-185 + reward_function.py:69-79 + uav_env.py:494-516 ----
+        r.last_step_bytes = 0.f;
+        float nx = r.x, ny = r.y;
+        if (action == 0)
+            ny += 1.0f;
+        else if (action == 1)
+            ny -= 1.0f;
+        else if (action == 2)
+            nx -= 1.0f;
+        else
+            nx += 1.0f;
+        const double before = r.battery;
+        const bool ok = (0.f <= nx) && (nx < (float)r.grid_w) && (0.f <= ny) && (ny < (float)r.grid_h);
+        if (ok) {
+            r.x = nx;
+            r.y = ny;
+            r.battery -= p.e_move;
+        } else {
+            r.battery -= p.e_fail;
+            r.boundary_hits += 1;
+        }
+        const Real used = (Real)(before - r.battery);
+        reward = p.p_step;
+        reward += ok ? p.r_move : p.p_boundary;
+        reward += p.p_battery * used;
+        reward += p.p_data_loss * step_loss;
+        compute_det(p, r, s);  // for the observation at the new position
+    } else {
+        // ---- uav_env.py:518-632 ----
+        float before[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) before[k] = s[k].active ? (float)(s[k].buf / p.rate) : 0.f;  // :386-394
+        r.battery -= p.e_hover;
+        const Real used = (Real)p.used_hover;
+        compute_det(p, r, s);
+        // Phase 2: ADR update, link probability, duty-cycle gate
+        unsigned att[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int j = lane + 32 * k;
+            bool a = false;
+            if (s[k].active && s[k].buf > Real(0)) {
+                Real da, db, u;
+                dr.collect_triple(j, da, db, u);
+                s[k].cur = s[k].det + da;
+                adr_update(p, s[k].cur, s[k].ema, s[k].sf);
+                const Real rb = s[k].det + db;
+                Real plink;
+                if (rb < p.thr) {
+                    plink = Real(0);
+                } else {
+                    const Real x = (rb - p.noise_floor) - (Real)required_snr_of(s[k].sf);
+                    if constexpr (kParity)
+                        plink = 1.0 / (1.0 + exp(-x));
+                    else
+                        plink = __fdividef(1.0f, 1.0f + __expf(-x));
+                }
+                a = (plink * p.duty_frac) > u;
+            }
+            s[k].attempt = a;
+            att[k] = __ballot_sync(kFull, a);
+        }
+        att_mask = (unsigned long long)att[0];
+        if (SPL > 1) att_mask |= (unsigned long long)att[SPL - 1] << 32;
+
+        // Phase 3+4: SF groups in first-appearance order; k==1 wins, k>1 collides unless the strongest
+        // beats the runner-up by the capture threshold; each winner is range-checked (draw C) and drained.
+        Real urg_list[6];
+        int nwin = 0;
+        unsigned long long remaining = att_mask;
+        while (remaining) {
+            const int i0 = __ffsll((long long)remaining) - 1;
+            int sf_sel[SPL];
+            unsigned long long gm = 0ull;
+            int sf0 = 0;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int v = shfl(s[k].sf, i0 & 31);
+                if ((i0 >> 5) == k) sf0 = v;
+            }
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                sf_sel[k] = s[k].attempt && s[k].sf == sf0;
+                gm |= (unsigned long long)__ballot_sync(kFull, sf_sel[k]) << (32 * k);
+            }
+            remaining &= ~gm;
+            const int cnt = __popcll(gm);
+            int winner = -1;
+            if (cnt == 1) {
+                winner = i0;
+            } else {
+                collisions += cnt - 1;
+                // strongest and runner-up by current_rssi (draw A)
+                Real v1 = Real(0);
+                int i1 = -1;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    if (sf_sel[k] && (i1 < 0 || s[k].cur > v1)) {
+                        v1 = s[k].cur;
+                        i1 = lane + 32 * k;
+                    }
+                }
+                Real top_v;
+                int top_i;
+                group_argmax(v1, i1, top_v, top_i);
+                Real v2 = Real(0);
+                int i2 = -1;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const int j = lane + 32 * k;
+                    if (sf_sel[k] && j != top_i && (i2 < 0 || s[k].cur > v2)) {
+                        v2 = s[k].cur;
+                        i2 = j;
+                    }
+                }
+                Real sec_v;
+                int sec_i;
+                group_argmax(v2, i2, sec_v, sec_i);
+                if (top_v > (sec_v + p.capture_db)) {
+                    winner = top_i;
+                    r.capture_triggers += 1;
+                }
+            }
+            if (winner >= 0) {
+                win_mask |= 1ull << winner;
+                // owner lane performs IoTSensor.collect_data (iot_sensors.py:127-145)
+                Real got = Real(0), urg_w = Real(0);
+                int in_range = 0;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    if (lane + 32 * k == winner) {
+                        const Real rc = s[k].det + dr.winner_draw(winner);
+                        in_range = rc >= p.thr;
+                        if (in_range && s[k].buf > Real(0)) {
+                            const Real cap = (Real)data_rate_of(s[k].sf) * p.cd;
+                            got = s[k].buf < cap ? s[k].buf : cap;
+                            s[k].buf -= got;
+                            s[k].tx += got;
+                        }
+                        urg_w = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], r.elapsed_s));
+                    }
+                }
+                const int owner = winner & 31;
+                got = shfl(got, owner);
+                urg_w = shfl(urg_w, owner);
+                in_range = shfl(in_range, owner);
+                urg_list[nwin < 6 ? nwin : 5] = urg_w;
+                nwin += 1;
+                if (in_range && got > Real(0)) {
+                    total_bytes += got;
+                    r.total_data_collected += (double)got;
+                    r.delivered += 1;
+                    const bool seen = winner < 32 ? (r.visited_lo >> winner) & 1u : (r.visited_hi >> (winner - 32)) & 1u;
+                    if (!seen) {
+                        any_new = true;
+                        if (winner < 32)
+                            r.visited_lo |= 1u << winner;
+                        else
+                            r.visited_hi |= 1u << (winner - 32);
+                    }
+                }
+            }
+        }
+        // Phase 5: fairness metrics (uav_env.py:596-604)
+        unsigned empty_b = 0u, nonempty_b = 0u;
+        float diff[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            empty_b |= __ballot_sync(kFull, s[k].active && s[k].buf <= Real(0));
+            nonempty_b |= __ballot_sync(kFull, s[k].active && !(s[k].buf <= Real(0)));
+            const float after = s[k].active ? (float)(s[k].buf / p.rate) : 0.f;
+            const float d = before[k] - after;
+            diff[k] = d > 0.f ? d : 0.f;
+        }
+        was_empty = empty_b != 0u;
+        all_collected = nonempty_b == 0u;
+        urg_red = (Real)sensor_sum<Real, SPL>(diff, N, lane, sc.red, kSumNumpy);  // float32 np.sum
+        r.last_step_bytes = (float)total_bytes;
+        if (nwin > 0) {  // np.mean over the winners, in SF first-appearance order (uav_env.py:610-615)
+            Real acc = Real(0);
+            for (int w = 0; w < nwin && w < 6; ++w) acc += urg_list[w];
+            mean_urg = acc / (Real)nwin;
+        }
+        // Phase 6: reward_function.py:81-128, same order of additions
+        reward = p.p_step + p.p_hover;
+        if (total_bytes > Real(0)) {
+            reward += p.r_per_byte * total_bytes * mean_urg;
+            if (any_new) reward += p.r_new;
+        }
+        if (urg_red > Real(0)) reward += p.r_urg_red * urg_red;
+        if (was_empty && total_bytes == Real(0)) reward += p.p_revisit;
+        reward += p.p_battery * used;
+        if (collisions > 0) reward += p.p_collision * (Real)collisions;
+        if (step_loss > Real(0)) reward += p.p_data_loss * step_loss;
+        if (N > 1) {  // calculate_starvation_penalty, reward_function.py:46-57
+            Real mx = Real(0);
+#pragma unroll
+            for (int k = 0; k < SPL; ++k)
+                if (s[k].active) mx = s[k].buf > mx ? s[k].buf : mx;
+            mx = warp_max(mx);
+            if (mx != Real(0)) {
+                Real nrm[SPL], dev[SPL];
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf / mx : Real(0);
+                const Real mean = sensor_sum<Real, SPL>(nrm, N, lane, sc.red, kSumNumpy) / (Real)N;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const Real d = nrm[k] - mean;
+                    dev[k] = s[k].active ? d * d : Real(0);
+                }
+                reward += p.p_starvation * (sensor_sum<Real, SPL>(dev, N, lane, sc.red, kSumNumpy) / (Real)N);
+            }
+        }
+        if (all_collected) reward += p.r_completion;
+        r.collisions += collisions;
+    }
+
+    // ---- uav_env.py:471-485: truncation + terminal penalties ----
+    bool truncated = false;
+    if (!(r.battery > p.batt_floor)) truncated = true;  // uav.py:224
+    if (r.step >= p.max_steps) truncated = true;
+    if (truncated) {
+        const int unvisited = N - (__popc(r.visited_lo) + __popc(r.visited_hi));
+        if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
+        int starved = 0;  // reward_function.py:59-67
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const Real g = generated_of(p, s[k], r.elapsed_s);
+            starved += __popc(__ballot_sync(kFull, s[k].active && g > Real(0) && (s[k].tx / g) < p.cr_thr));
+        }
+        Real pen = Real(0);
+        for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
+        reward += pen;
+    }
+    r.total_reward += (double)reward;
+
+    // ---- observation (uav_env.py:638-674) ----
+    float* obs_row = b.obs + (size_t)e * p.obs_stride;
+    observe<Real, REPLAY, SPL>(p, r, s, dr, lane, sc.obs, obs_row);
+
+    // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
+    Real shaped = reward;
+    if (p.domain_rand) {
+        const float cur = nearest_with_data(r, s);
+        if (prev_dist > 0.f) {
+            if constexpr (kParity)
+                shaped += p.prox_eta * ((double)prev_dist - (double)cur);
+            else
+                shaped += p.prox_eta * (prev_dist - cur);
+        }
+        r.prev_dist_nearest = cur;
+        if (r.first_full_coverage_step < 0 && (__popc(r.visited_lo) + __popc(r.visited_hi)) == N)
+            r.first_full_coverage_step = r.step;
+        Real r1[SPL], r2[SPL];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const Real g = generated_of(p, s[k], r.elapsed_s);
+            const bool has = s[k].active && g > Real(0);
+            const Real rate = has ? (s[k].tx / g) * Real(100) : Real(0);
+            r1[k] = rate;
+            r2[k] = rate * rate;
+            cnt += __popc(__ballot_sync(kFull, has));
+        }
+        if (cnt > 0) {
+            const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, sc.red, kSumSequential);
+            const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, sc.red, kSumSequential);
+            const Real jain = s2 > Real(0) ? (s1 * s1) / ((Real)cnt * s2) : Real(1);
+            shaped += p.jain_bonus * (jain - Real(0.5)) / (Real)N;
+        }
+    }
+    r.episode_return += (double)shaped;
+
+    // ---- outputs ----
+    if (lane == 0) {
+        reinterpret_cast<Real*>(b.reward)[e] = shaped;
+        b.done[e] = truncated ? 1 : 0;
+        if (b.step_detail) {
+            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+            d[UAVSIM_DETAIL_COLLISIONS] = collisions;
+            d[UAVSIM_DETAIL_BYTES] = (double)total_bytes;
+            d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)urg_red;
+            d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)mean_urg;
+            d[UAVSIM_DETAIL_WAS_NEW] = any_new;
+            d[UAVSIM_DETAIL_WAS_EMPTY] = was_empty;
+            d[UAVSIM_DETAIL_ALL_COLLECTED] = all_collected;
+            d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)att_mask;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(att_mask >> 32);
+            d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)win_mask;
+            d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(win_mask >> 32);
+            d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
+            d[UAVSIM_DETAIL_TRUNCATED] = truncated;
+            d[14] = 0.0;
+            d[15] = 0.0;
+        }
+    }
+
+    // ---- SB3 VecEnv semantics: finished episodes restart inside the same call ----
+    bool layout_changed = false;
+    if (truncated && p.auto_reset) {
+        if (b.terminal_obs) {
+            const int n = 3 + p.fps * N;
+            float* t = b.terminal_obs + (size_t)e * p.obs_dim;
+            for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? sc.obs[i] : 0.0f;
+        }
+        write_episode_stats<Real, SPL>(p, b, e, lane, r, s);
+        reset_env<Real, REPLAY, SPL>(p, b, e, lane, r, s, sc, layout_changed, (Real*)nullptr);
+        r.episode += 1;
+    } else if (b.action_mask && lane == 0) {
+        b.action_mask[e] = action_mask_of(r.x, r.y, r.grid_w, r.grid_h);
+    }
+
+    store_sensors<Real, SPL>(b, p, e, lane, s, (truncated && p.auto_reset));
+    if (lane == 0) b.rec[e] = r;
+}
+
+}  // namespace uavsim

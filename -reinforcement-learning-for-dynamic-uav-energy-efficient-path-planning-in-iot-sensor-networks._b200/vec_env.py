@@ -1,0 +1,469 @@
+"""Host-side mirror of the reference interface for the batched step.
+
+`UAVVecEnv` stands where the reference has
+
+    DummyVecEnv([lambda: Monitor(DomainRandEnv(...))] * 4)      # dqn.py:1223-1234, 1276
+    UAVEnvironment(grid_size=..., num_sensors=..., **ENV_BASE)  # sweep_eval.py:462
+
+i.e. it keeps the constructor keywords of `UAVEnvironment.__init__` (uav_env.py:266-287)
+and of `DomainRandEnv.__init__` (dqn.py:202-232), the Gymnasium reset/step/observation/
+reward semantics, and the stable-baselines3 2.7 `VecEnv` surface the reference's call sites
+use: `reset() -> obs`, `step(actions) -> (obs, rewards, dones, infos)`
+with numpy arrays, `step_async/step_wait`, auto-reset with `terminal_observation` /
+`TimeLimit.truncated` / Monitor's `episode` entry, `get_attr("last_episode_stats")`,
+`env_method("set_curriculum_stage", s)`, `seed`, `close`.
+
+All simulation state lives in one torch-allocated device arena that libuavsim.so borrows;
+`reset_tensors()/step_tensors()` return the bound CUDA tensors themselves (zero-copy), the
+numpy methods add exactly one device->host copy per output.  There is no CPU implementation
+behind this class: without a CUDA device construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .spaces import Box, Discrete
+
+# dqn.py:63-69 -- grids per curriculum stage (sensor counts are fixed per worker)
+CURRICULUM_STAGES = [
+    [(100, 100)],
+    [(100, 100), (200, 200)],
+    [(100, 100), (200, 200), (300, 300)],
+    [(100, 100), (200, 200), (300, 300), (400, 400)],
+    [(100, 100), (200, 200), (300, 300), (400, 400), (500, 500)],
+]
+MAX_SENSORS_LIMIT = 50  # dqn.py:121
+
+_INFO_KEYS = ("uav_position", "battery", "battery_percent", "sensors_collected", "current_step",
+              "total_reward", "total_data_collected", "coverage_percentage", "is_alive", "max_urgency",
+              "avg_urgency", "high_urgency_sensors", "capture_effect_triggers", "boundary_hits",
+              "edge_steps", "last_step_bytes_collected", "sensor_collection_ratios")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class UAVVecEnv:
+    """E batched UAV-LoRa environments on one GPU.
+
+    Reference constructor keywords keep their names and meaning (uav_env.py:266-287):
+    grid_size, sensor_positions, num_sensors, data_generation_rate, max_buffer_size,
+    rssi_threshold, sensor_duty_cycle, uav_start_position, max_battery, collection_duration,
+    max_steps, penalty_data_loss, reward_urgency_reduction, penalty_battery, reward_movement,
+    include_sensor_positions.  `lora_spreading_factor` and `path_loss_exponent` are accepted and
+    ignored exactly as the reference ignores them (iot_sensors.py:309 forces SF12 on reset,
+    calculate_rssi never reads the exponent).
+    """
+
+    def __init__(self, num_envs: int, grid_size=(500, 500), num_sensors=20, *,
+                 sensor_positions=None, data_generation_rate=22.0 / 10, max_buffer_size=1000.0,
+                 lora_spreading_factor=7, path_loss_exponent=2.0, rssi_threshold=-85.0,
+                 sensor_duty_cycle=10.0, uav_start_position=None, max_battery=274.0,
+                 collection_duration=1.0, max_steps=2100, render_mode=None,
+                 penalty_data_loss=-1.0, reward_urgency_reduction=20.0, penalty_battery=-0.5,
+                 reward_movement=10.0, include_sensor_positions=False,
+                 # batched-simulator arguments
+                 max_sensors: Optional[int] = None, obs_slots: Optional[int] = None,
+                 domain_randomisation=False, curriculum_stage=0,
+                 precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
+                 device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope (uav_env.py:706-888)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("UAVVecEnv needs a CUDA device: the batched step has no CPU fallback")
+        self.lib = N.load()
+        self.device = torch.device(device)
+        self.num_envs = int(num_envs)
+        ns = np.broadcast_to(np.asarray(num_sensors, dtype=np.int32), (self.num_envs,)).copy()
+        self._num_sensors = ns
+        P = int(max_sensors if max_sensors is not None else ns.max())
+        cfg = N.default_config()
+        cfg.num_envs = self.num_envs
+        cfg.max_sensors = P
+        cfg.obs_slots = int(obs_slots if obs_slots is not None else
+                            (MAX_SENSORS_LIMIT if domain_randomisation and P <= MAX_SENSORS_LIMIT else P))
+        cfg.features_per_sensor = 5 if include_sensor_positions else 3
+        cfg.precision = {"f64": N.F64, "f32": N.F32}[precision]
+        cfg.rng_mode = {"replay": N.RNG_REPLAY, "philox": N.RNG_PHILOX}[rng]
+        cfg.reset_mode = N.RESET_DOMAIN_RAND if domain_randomisation else N.RESET_FIXED
+        cfg.auto_reset = int(bool(auto_reset))
+        cfg.seed = int(seed) & (2 ** 64 - 1)
+        cfg.env_id_offset = int(env_id_offset)
+        grids = np.asarray(grid_size, dtype=np.int32)
+        per_env_grid = grids.ndim == 2
+        g0 = grids[0] if per_env_grid else grids
+        if domain_randomisation:
+            g0 = np.asarray(CURRICULUM_STAGES[0][0], dtype=np.int32)   # dqn.py:216-218 init grid
+        cfg.grid_w, cfg.grid_h = int(g0[0]), int(g0[1])
+        cfg.num_sensors = int(ns[0])
+        cfg.max_steps = int(max_steps)
+        cfg.data_generation_rate = float(data_generation_rate)
+        cfg.max_buffer_size = float(max_buffer_size)
+        cfg.rssi_threshold = float(rssi_threshold)
+        cfg.duty_cycle = float(sensor_duty_cycle)
+        cfg.max_battery = float(max_battery)
+        cfg.collection_duration = float(collection_duration)
+        start = (0.0, 0.0) if uav_start_position is None else uav_start_position
+        starts = np.asarray(start, dtype=np.float32)
+        per_env_start = starts.ndim == 2
+        s0 = starts[0] if per_env_start else starts
+        cfg.start_x, cfg.start_y = float(s0[0]), float(s0[1])
+        cfg.penalty_data_loss = float(penalty_data_loss)
+        cfg.reward_urgency_reduction = float(reward_urgency_reduction)
+        cfg.penalty_battery = float(penalty_battery)
+        cfg.reward_movement = float(reward_movement)
+        self._stage = -1
+        self.cfg = cfg
+        self.domain_randomisation = bool(domain_randomisation)
+        if domain_randomisation:
+            self._apply_stage(cfg, curriculum_stage)
+        self.dims = N.query_dims(cfg)
+        self.precision = precision
+        self.real_dtype = torch.float64 if precision == "f64" else torch.float32
+
+        E, dev = self.num_envs, self.device
+        with torch.cuda.device(dev):
+            self._arena = torch.empty(self.dims.arena_bytes, dtype=torch.uint8, device=dev)
+            assert self._arena.data_ptr() % 256 == 0
+            h = C.c_void_p()
+            N.check(self.lib.uavsim_create(C.byref(cfg), _ptr(self._arena), self._arena.numel(),
+                                           self._stream(), C.byref(h)))
+            self._h = h
+            self.obs = torch.empty((E, self.dims.obs_dim), dtype=torch.float32, device=dev)
+            self.reward = torch.empty((E,), dtype=self.real_dtype, device=dev)
+            self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
+            self.terminal_obs = torch.zeros((E, self.dims.obs_dim), dtype=torch.float32, device=dev)
+            self.episode_stats = torch.zeros((E, N.STAT_COUNT), dtype=torch.float64, device=dev)
+            self.action_mask = torch.zeros((E,), dtype=torch.uint8, device=dev) if action_mask else None
+            self.step_detail = (torch.zeros((E, N.DETAIL_COUNT), dtype=torch.float64, device=dev)
+                                if step_detail else None)
+            self.draw_export = (torch.full((E, N.NUM_SLOTS, P), float("nan"), dtype=self.real_dtype, device=dev)
+                                if export_draws else None)
+            out = N.Outputs(_ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.terminal_obs),
+                            _ptr(self.episode_stats), _ptr(self.action_mask), _ptr(self.step_detail),
+                            _ptr(self.draw_export))
+            N.check(self.lib.uavsim_bind_outputs(self._h, C.byref(out), self._stream()))
+            self._fields = {f: self._field_tensor(f) for f in range(5)}
+            sums = C.c_void_p()
+            N.check(self.lib.uavsim_stat_sums(self._h, C.byref(sums)))
+            off = sums.value - self._arena.data_ptr()
+            self.stat_sums = self._arena[off: off + 8 * N.STAT_SUMS].view(torch.float64)
+            # scenario: injected layout / per-env grids / starts, else Philox uniform layouts
+            sc_xy = None
+            if sensor_positions is not None:
+                xy = np.asarray(sensor_positions, dtype=np.float32)
+                if xy.ndim == 2:
+                    xy = np.broadcast_to(xy[None], (E,) + xy.shape)
+                full = np.zeros((E, P, 2), dtype=np.float32)
+                full[:, : xy.shape[1]] = xy
+                sc_xy = full
+            self.set_scenario(sensor_xy=sc_xy,
+                              num_sensors=ns if (ns != ns[0]).any() else None,
+                              grid_wh=grids if per_env_grid else None,
+                              start_xy=starts if per_env_start else None)
+            if sensor_positions is None:
+                N.check(self.lib.uavsim_generate_layouts(self._h, self._stream()))
+        self._replay_keep = {}
+        self._actions_dev = torch.zeros((E,), dtype=torch.int32, device=dev)
+        self._pending_actions = None
+        self._host = None
+        self.last_episode_stats = [None] * E
+        self.observation_space = Box(low=-np.inf if domain_randomisation else -1.0,
+                                     high=np.inf if domain_randomisation else 1.0,
+                                     shape=(self.dims.obs_dim,), dtype=np.float32)
+        self.action_space = Discrete(N.NUM_ACTIONS)
+        self.render_mode = None
+        self.metadata = {"render_modes": []}
+        self._closed = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _field_tensor(self, field):
+        v = N.FieldView()
+        N.check(self.lib.uavsim_get_field(self._h, field, C.byref(v)))
+        shape = [v.shape[i] for i in range(v.ndim)]
+        nbytes = int(np.prod(shape)) * v.elem_bytes
+        off = v.ptr - self._arena.data_ptr()
+        raw = self._arena[off: off + nbytes]
+        if v.is_float == 2:
+            return raw.view(self.num_envs, v.elem_bytes)
+        dt = {(1, 8): torch.float64, (1, 4): torch.float32, (0, 1): torch.uint8}[(v.is_float, v.elem_bytes)]
+        return raw.view(dt).view(*shape)
+
+    def _apply_stage(self, cfg, stage):
+        stage = int(np.clip(stage, 0, len(CURRICULUM_STAGES) - 1))      # dqn.py:265
+        grids = CURRICULUM_STAGES[stage]
+        cfg.num_grids = len(grids)
+        for i, (w, h) in enumerate(grids):
+            cfg.grids[i][0], cfg.grids[i][1] = w, h
+        self._stage = stage
+        return grids
+
+    # ------------------------------------------------------------------ scenario / replay
+    def set_scenario(self, sensor_xy=None, num_sensors=None, grid_wh=None, start_xy=None):
+        """Inject per-env layouts (the `sensor_positions=` / `uav_start_position=` ctor arguments)."""
+        dev = self.device
+
+        def up(a, dt):
+            return None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev).contiguous()
+        keep = [up(sensor_xy, torch.float32), up(num_sensors, torch.int32), up(grid_wh, torch.int32),
+                up(start_xy, torch.float32)]
+        if all(k is None for k in keep):
+            return
+        if keep[0] is not None:
+            assert tuple(keep[0].shape) == (self.num_envs, self.cfg.max_sensors, 2)
+        sc = N.Scenario(*[_ptr(k) for k in keep])
+        with torch.cuda.device(dev):
+            N.check(self.lib.uavsim_set_scenario(self._h, C.byref(sc), self._stream()))
+            torch.cuda.current_stream(dev).synchronize()
+        if num_sensors is not None:
+            self._num_sensors = np.asarray(num_sensors, dtype=np.int32).copy()
+
+    def set_replay(self, step_draws=None, reset_draws=None, reset_fill=None, reset_init_sf=None,
+                   reset_sensor_xy=None, reset_num_sensors=None, reset_grid_wh=None, reset_start_xy=None):
+        """Bind slot-addressed draw tables (device float64 tensors or numpy arrays); see
+        include/uavsim.h `uavsim_replay`.  Arguments left None keep their previous binding."""
+        dev = self.device
+
+        def up(name, a, dt):
+            if a is None:
+                return self._replay_keep.get(name)
+            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+            t = t.to(device=dev, dtype=dt).contiguous()
+            self._replay_keep[name] = t
+            return t
+        E, P = self.num_envs, self.cfg.max_sensors
+        sd = up("step_draws", step_draws, torch.float64)
+        rd = up("reset_draws", reset_draws, torch.float64)
+        rf = up("reset_fill", reset_fill, torch.float64)
+        ri = up("reset_init_sf", reset_init_sf, torch.int32)
+        rxy = up("rs_xy", reset_sensor_xy, torch.float32)
+        rn = up("rs_n", reset_num_sensors, torch.int32)
+        rg = up("rs_g", reset_grid_wh, torch.int32)
+        rs = up("rs_s", reset_start_xy, torch.float32)
+        for t in (sd, rd):
+            assert t is None or tuple(t.shape) == (E, N.NUM_SLOTS, P), "draw tables are [E, 6, P]"
+        assert rf is None or tuple(rf.shape) == (E, P)
+        rp = N.Replay(_ptr(sd), _ptr(rd), _ptr(rf), _ptr(ri), N.Scenario(_ptr(rxy), _ptr(rn), _ptr(rg), _ptr(rs)))
+        N.check(self.lib.uavsim_set_replay(self._h, C.byref(rp)))
+
+    # ------------------------------------------------------------------ zero-copy tensor API
+    def reset_tensors(self, env_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Gymnasium reset for all (or the masked) envs; returns the bound obs tensor [E, obs_dim]."""
+        with torch.cuda.device(self.device):
+            m = None
+            if env_mask is not None:
+                m = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            N.check(self.lib.uavsim_reset(self._h, _ptr(m), self._stream()))
+        return self.obs
+
+    def step_tensors(self, actions: torch.Tensor):
+        """One step for every env.  `actions`: int32 CUDA tensor [E] in [0, 4].  Returns the bound
+        (obs, reward, done) CUDA tensors -- overwritten in place by the next call.  Asynchronous:
+        invalid actions are reported by `poll_errors()`."""
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_step(self._h, _ptr(actions), self._stream()))
+        return self.obs, self.reward, self.done
+
+    def poll_errors(self):
+        """Raises ValueError if any step since the last poll saw an action outside [0, 4]
+        (uav_env.py:468).  Synchronises the stream."""
+        first = C.c_int64(-1)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_poll_error(self._h, self._stream(), C.byref(first)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.uavsim_launch_count(self._h))
+
+    def state(self) -> dict:
+        """Zero-copy views of the structure-of-arrays state in HBM."""
+        st = self._fields[N.FIELD_SENSOR_STATE]
+        return dict(records=self._fields[N.FIELD_ENV_RECORD], buffer=st[..., 0], transmitted=st[..., 1],
+                    lost=st[..., 2], avg_rssi=st[..., 3], sensor_pos=self._fields[N.FIELD_SENSOR_POS],
+                    generated_base=self._fields[N.FIELD_SENSOR_GEN], spreading_factor=self._fields[N.FIELD_SENSOR_SF])
+
+    def records(self) -> np.ndarray:
+        """Host copy of the per-env records as a numpy structured array (uavsim_env_record)."""
+        raw = self._fields[N.FIELD_ENV_RECORD].cpu().numpy()
+        return raw.view(np.dtype(N.ENV_RECORD_DTYPE)).reshape(self.num_envs)
+
+    def generated(self) -> torch.Tensor:
+        """total_data_generated per sensor [E, P] (iot_sensors.py:116)."""
+        g = self._fields[N.FIELD_SENSOR_GEN]
+        if self.precision == "f64":
+            return g
+        el = torch.as_tensor(self.records()["elapsed_s"], device=self.device)
+        return g + float(self.cfg.data_generation_rate) * el[:, None]
+
+    def snapshot(self) -> torch.Tensor:
+        """Checkpoint of ALL simulation state (one device copy of the arena)."""
+        return self._arena.clone()
+
+    def restore(self, snap: torch.Tensor):
+        self._arena.copy_(snap)
+
+    # ------------------------------------------------------------------ SB3 VecEnv / Gymnasium-vector API
+    def reset(self, seed=None, options=None) -> np.ndarray:
+        if seed is not None:
+            self.seed(seed)
+        obs = self.reset_tensors()
+        return obs.cpu().numpy()
+
+    def step_async(self, actions) -> None:
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (%d,)" % self.num_envs)
+        if ((a < 0) | (a > 4)).any():
+            bad = int(np.flatnonzero((a < 0) | (a > 4))[0])
+            raise ValueError("Invalid action: %r" % (a[bad],))          # uav_env.py:468
+        self._pending_actions = torch.as_tensor(a.astype(np.int32, copy=False))
+
+    def step_wait(self):
+        if self._pending_actions is None:
+            raise RuntimeError("step_wait() without step_async()")
+        self._actions_dev.copy_(self._pending_actions, non_blocking=False)
+        self._pending_actions = None
+        self.step_tensors(self._actions_dev)
+        obs = self.obs.cpu().numpy()
+        rew = self.reward.cpu().numpy()
+        dones = self.done.cpu().numpy().astype(bool)
+        infos = [{} for _ in range(self.num_envs)]
+        idx = np.flatnonzero(dones)
+        if idx.size:
+            didx = torch.as_tensor(idx, device=self.device)
+            stats = self.episode_stats[didx].cpu().numpy()
+            tobs = self.terminal_obs[didx].cpu().numpy() if self.cfg.auto_reset else None
+            for k, e in enumerate(idx):
+                st = dict(zip(N.STAT_NAMES, stats[k].tolist()))
+                info = infos[e]
+                info["TimeLimit.truncated"] = True        # terminated is never True (uav_env.py:471)
+                if tobs is not None:
+                    info["terminal_observation"] = tobs[k]
+                    info["episode"] = {"r": st["return"], "l": int(st["length"])}   # Monitor
+                    self.last_episode_stats[e] = self._episode_dict(st)
+        return obs, rew, dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    @staticmethod
+    def _episode_dict(st):
+        """DomainRandEnv.last_episode_stats (dqn.py:316-331)."""
+        ttc = st["time_to_coverage"]
+        return {"total_generated": st["total_generated"], "total_collected": st["total_collected"],
+                "total_lost": st["total_lost"], "battery_remaining": st["battery_remaining"],
+                "ndr": st["ndr"], "fairness_std": st["fairness_std"], "jains_index": st["jains_index"],
+                "grid_size": (int(st["grid_w"]), int(st["grid_h"])), "num_sensors": int(st["num_sensors"]),
+                "data_efficiency": st["data_efficiency"], "bytes_per_wh": st["bytes_per_wh"],
+                "time_to_coverage": None if ttc < 0 else int(ttc)}
+
+    def get_info(self, indices=None) -> list:
+        """The reference's `_get_info()` dict (uav_env.py:676-700) for the requested envs, computed
+        on the host from one copy of the state columns."""
+        idx = self._indices(indices)
+        rec = self.records()
+        st = self.state()
+        buf = st["buffer"].cpu().numpy().astype(np.float64)
+        tx = st["transmitted"].cpu().numpy().astype(np.float64)
+        gen = self.generated().cpu().numpy().astype(np.float64)
+        out = []
+        rate = float(self.cfg.data_generation_rate)
+        for e in idx:
+            r = rec[e]
+            n = int(r["num_sensors"])
+            aoi = (buf[e, :n] / rate).astype(np.float32)
+            nv = bin(int(r["visited_lo"])).count("1") + bin(int(r["visited_hi"])).count("1")
+            out.append({
+                "uav_position": np.array([r["x"], r["y"]], dtype=np.float32),
+                "battery": float(r["battery"]),
+                "battery_percent": float(r["battery"]) / float(self.cfg.max_battery) * 100,
+                "sensors_collected": nv, "current_step": int(r["step"]),
+                "total_reward": float(r["total_reward"]),
+                "total_data_collected": float(r["total_data_collected"]),
+                "coverage_percentage": nv / n * 100,
+                "is_alive": bool(r["battery"] > 0.02 * float(self.cfg.max_battery)),
+                "max_urgency": float(np.max(aoi)), "avg_urgency": float(np.mean(aoi)),
+                "high_urgency_sensors": int(np.sum(aoi > 0.8)),
+                "capture_effect_triggers": int(r["capture_triggers"]),
+                "boundary_hits": int(r["boundary_hits"]), "edge_steps": int(r["edge_steps"]),
+                "last_step_bytes_collected": float(r["last_step_bytes"]),
+                "sensor_collection_ratios": [float(tx[e, i] / max(gen[e, i], 1e-6)) for i in range(n)],
+            })
+        return out
+
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    def get_attr(self, attr_name: str, indices=None) -> list:
+        idx = self._indices(indices)
+        if attr_name == "last_episode_stats":
+            return [self.last_episode_stats[i] for i in idx]
+        if attr_name == "num_sensors":
+            return [int(self._num_sensors[i]) for i in idx]
+        if attr_name == "grid_size":
+            rec = self.records()
+            return [(int(rec[i]["grid_w"]), int(rec[i]["grid_h"])) for i in idx]
+        if attr_name in ("_curriculum_stage", "curriculum_stage"):
+            return [self._stage for _ in idx]
+        if attr_name == "render_mode":
+            return [None for _ in idx]
+        if hasattr(self, attr_name):
+            return [getattr(self, attr_name) for _ in idx]
+        raise AttributeError(attr_name)
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        if attr_name in ("_curriculum_stage", "curriculum_stage"):
+            self.set_curriculum_stage(value)
+        else:
+            raise AttributeError("cannot set %r on the batched environment" % attr_name)
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> list:
+        idx = self._indices(indices)
+        if method_name == "set_curriculum_stage":           # dqn.py:921-926
+            self.set_curriculum_stage(*args, **kwargs)
+            return [None for _ in idx]
+        if method_name in ("get_info", "_get_info"):
+            return self.get_info(idx)
+        raise AttributeError(method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> list:
+        return [False for _ in self._indices(indices)]
+
+    def set_curriculum_stage(self, stage: int):
+        """DomainRandEnv.set_curriculum_stage (dqn.py:258-277): later resets sample grids from it."""
+        grids = self._apply_stage(self.cfg, stage)
+        flat = (C.c_int32 * (2 * len(grids)))(*[v for g in grids for v in g])
+        N.check(self.lib.uavsim_set_stage_grids(self._h, len(grids), flat))
+
+    def seed(self, seed: Optional[int] = None) -> Sequence[Optional[int]]:
+        """The Philox key is fixed at construction; SB3 calls seed() once before the first reset.
+        Returned values are the per-env global ids the streams are keyed on."""
+        return [int(self.cfg.env_id_offset) + i for i in range(self.num_envs)]
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self.lib.uavsim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -275,6 +275,26 @@ class UAVVecEnv:
             N.check(self.lib.uavsim_step(self._h, _ptr(actions), self._stream()))
         return self.obs, self.reward, self.done
 
+    def make_host_buffers(self):
+        """Pinned host buffers for `step_host` (actions in; obs, reward, done out)."""
+        E = self.num_envs
+        return dict(actions=torch.zeros((E,), dtype=torch.int32).pin_memory(),
+                    obs=torch.empty((E, self.dims.obs_dim), dtype=torch.float32).pin_memory(),
+                    reward=torch.empty((E,), dtype=self.real_dtype).pin_memory(),
+                    done=torch.empty((E,), dtype=torch.uint8).pin_memory())
+
+    def step_host(self, host: dict, copy_obs=True):
+        """The end-to-end call with HOST buffers (uavsim_step_host): actions host->device, one step,
+        obs/reward/done device->host, stream synchronised on return.  Actions are validated on the
+        host first, as the reference raises ValueError before doing anything useful (uav_env.py:468)."""
+        a = host["actions"]
+        if bool(((a < 0) | (a > 4)).any()):
+            raise ValueError("Invalid action")
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_step_host(self._h, _ptr(a), _ptr(host["obs"]) if copy_obs else None,
+                                              _ptr(host["reward"]), _ptr(host["done"]), self._stream()))
+        return host["obs"], host["reward"], host["done"]
+
     def poll_errors(self):
         """Raises ValueError if any step since the last poll saw an action outside [0, 4]
         (uav_env.py:468).  Synchronises the stream."""

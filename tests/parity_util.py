@@ -114,7 +114,8 @@ def compare_step(co, env, tag, acc, float_tol=None):
     flt("total_reward", r["total_reward"], oe["total_reward"])
     flt("episode_return", r["episode_return"], oe["episode_return"])
     flt("total_data_collected", r["total_data_collected"], oe["total_data_collected"])
-    flt("prev_dist", r["prev_dist_nearest"], oe["prev_dist_nearest"].astype(np.float32))
+    if co.p.domain_rand:   # DomainRandEnv._prev_dist_nearest only exists in the wrapper
+        flt("prev_dist", r["prev_dist_nearest"], oe["prev_dist_nearest"].astype(np.float32))
     for k in ("buf", "tx", "lost", "ema", "gen"):
         flt(k, g[k], oe[k][:, :P], live)
     # buffer-empty / saturation decisions are discrete

@@ -155,6 +155,7 @@ Params<Real> make_params(const uavsim_config& c) {
     p.e_fail = ((c.power_move_w * 0.5) * 1) / 3600;            // uav.py:125,182-183
     p.e_hover = (c.power_hover_w * c.collection_duration) / 3600;          // uav.py:205
     p.used_hover = (c.power_hover_w / (60 * 60)) * c.collection_duration;  // uav.py:263, uav_env.py:530
+    p.inv_max_battery = (float)(1.0 / c.max_battery);
     p.min_start_dist = c.min_start_dist;
     p.max_steps = c.max_steps;
     p.init_sf = c.init_sf;

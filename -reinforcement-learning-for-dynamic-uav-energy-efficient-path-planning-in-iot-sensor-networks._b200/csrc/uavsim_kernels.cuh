@@ -22,6 +22,11 @@
 //   REPLAY : true  = every random draw is read from a slot-addressed table (parity tests),
 //            false = counter-based Philox4x32-10.
 //   SPL    : sensor slots per lane (1: P <= 32, 2: P <= 64).
+// Execution shape: persistent warps (grid = SMs x resident blocks, each warp walks environments with a
+// grid stride), the 128-byte environment record moves through shared memory with one coalesced
+// load/store per step, inactive lanes run the same arithmetic and are masked at reductions and stores
+// (no divergent branches in the per-sensor code), every draw of a step is produced up front with one
+// Philox call serving both of a lane's sensor slots.
 // so the code that is parity-checked bit-for-bit against the oracle is the same source as the code
 // that is benchmarked.  There is no tensor-core work here: the path is elementwise + warp
 // reductions and is bounded by HBM traffic (DESIGN.md has the byte model).
@@ -64,6 +69,7 @@ struct Params {
     Real prox_eta, jain_bonus;
     // UAV energy (always float64: a handful of per-env scalars)
     double max_battery, batt_floor, e_move, e_fail, e_hover, used_hover;
+    float inv_max_battery;
     double min_start_dist;
     int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
     int32_t grids[UAVSIM_MAX_GRIDS][2];
@@ -161,6 +167,15 @@ __device__ __forceinline__ T np_pairwise(const T* a, int n) {
     return res;
 }
 
+// a / b: IEEE division in the parity build, MUFU.RCP-based __fdividef in the throughput build
+template <typename Real>
+__device__ __forceinline__ Real fdiv(Real a, Real b) {
+    if constexpr (std::is_same<Real, double>::value)
+        return a / b;
+    else
+        return __fdividef(a, b);
+}
+
 enum SumOrder { kSumNumpy, kSumSequential };
 
 // Sum of one value per sensor slot over the N real sensors of this warp's environment.
@@ -195,28 +210,32 @@ __device__ __forceinline__ T sensor_sum(const T (&v)[SPL], int N, int lane, doub
     }
 }
 
-__device__ __forceinline__ double data_rate_of(int sf) {  // iot_sensors.py:13-20
+template <typename Real>
+__device__ __forceinline__ Real data_rate_of(int sf) {  // iot_sensors.py:13-20
     switch (sf) {
-        case 7: return 5470 / 8.0;
-        case 8: return 3125 / 8.0;
-        case 9: return 1760 / 8.0;
-        case 10: return 980 / 8.0;
-        case 11: return 440 / 8.0;
-        default: return 250 / 8.0;
+        case 7: return Real(5470 / 8.0);
+        case 8: return Real(3125 / 8.0);
+        case 9: return Real(1760 / 8.0);
+        case 10: return Real(980 / 8.0);
+        case 11: return Real(440 / 8.0);
+        default: return Real(250 / 8.0);
     }
 }
-__device__ __forceinline__ double required_snr_of(int sf) {  // iot_sensors.py:22-29 (:199-200 default)
+template <typename Real>
+__device__ __forceinline__ Real required_snr_of(int sf) {  // iot_sensors.py:22-29 (:199-200 default)
     switch (sf) {
-        case 7: return -6.0;
-        case 8: return -9.0;
-        case 9: return -12.0;
-        case 10: return -15.0;
-        case 11: return -17.5;
-        case 12: return -20.0;
-        default: return 7.5;
+        case 7: return Real(-6.0);
+        case 8: return Real(-9.0);
+        case 9: return Real(-12.0);
+        case 10: return Real(-15.0);
+        case 11: return Real(-17.5);
+        case 12: return Real(-20.0);
+        default: return Real(7.5);
     }
 }
+template <typename Real>
 __device__ __forceinline__ float link_quality_of(int sf) {  // uav_env.py:647
+    if constexpr (!std::is_same<Real, double>::value) return sf >= 12 ? 0.1f : (float)(12 - sf) * 0.2f;
     switch (sf) {
         case 7: return 1.0f;
         case 8: return 0.8f;
@@ -277,8 +296,8 @@ __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Rea
 // UAVEnvironment._calculate_urgency (uav_env.py:376-384)
 template <typename Real>
 __device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real lost, Real gen) {
-    const Real util = buf / p.maxbuf;
-    const Real lr = gen > Real(0) ? lost / gen : Real(0);
+    const Real util = fdiv(buf, p.maxbuf);
+    const Real lr = gen > Real(0) ? fdiv(lost, gen) : Real(0);
     const Real u = util * (Real(1) + lr * Real(10));
     return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
 }
@@ -315,72 +334,140 @@ __device__ __forceinline__ Real u01(uint32_t a) {
         return fminf(fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
 }
 
-template <typename Real, bool REPLAY>
+// All draws one step makes on this lane's sensor slots, produced up front.
+template <typename Real, int SPL>
+struct StepDraws {
+    Real d[SPL], e[SPL];           // observation: ADR draw, range draw      (uav_env.py:654-660)
+    Real a[SPL], b[SPL], u[SPL];   // collect: ADR draw, link draw, uniform  (uav_env.py:535-551)
+};
+
+// REPLAY: slot-addressed table [6][P] of this environment.
+// PHILOX: counter = (env id, stream | env hi, episode, step << 8 | lane << 3 | call).  One Philox4x32-10
+// call yields four words = two Box-Muller pairs, so with two sensor slots per lane a MOVE step costs ONE
+// call per lane (D,E for both slots) and a COLLECT step three (+ D,E | A,B | U,U); with one slot per lane
+// one and two.  The winner's range-check draw C is generated lazily by the owning lane (call 4 + slot).
+template <typename Real, bool REPLAY, int SPL>
 struct Draws {
-    const double* tab;  // replay: this env's [6][P] table
-    Real* exp;          // optional export of the draws actually used, [6][P]
+    const double* tab;
+    Real* exp;  // optional export of the draws actually used, [6][P]
     int P;
     uint32_t k0, k1, env_lo, env_hi, episode, step;
     Real sigma;
 
+    __device__ __forceinline__ Philox4 call(int lane, uint32_t c) const {
+        return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c, k0, k1);
+    }
     __device__ __forceinline__ void put(int slot, int j, Real v) const {
-        if (exp) exp[slot * P + j] = v;
+        if (exp && j < P) exp[slot * P + j] = v;
     }
-    __device__ __forceinline__ Philox4 call(uint32_t stream, int j, int c) const {
-        return philox4x32_10(env_lo, env_hi | (stream << 24), episode, (step << 7) | ((uint32_t)j << 1) | (uint32_t)c, k0,
-                             k1);
-    }
-    // observation draws D (ADR) and E (range check): uav_env.py:654-660
-    __device__ __forceinline__ void obs_pair(int j, Real& d, Real& e) const {
+    __device__ __forceinline__ void generate(int lane, bool collect, StepDraws<Real, SPL>& o) const {
         if constexpr (REPLAY) {
-            d = (Real)tab[UAVSIM_SLOT_D * P + j];
-            e = (Real)tab[UAVSIM_SLOT_E * P + j];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                const bool in = j < P;
+                o.d[k] = in ? (Real)tab[UAVSIM_SLOT_D * P + j] : Real(0);
+                o.e[k] = in ? (Real)tab[UAVSIM_SLOT_E * P + j] : Real(0);
+                o.a[k] = o.b[k] = o.u[k] = Real(0);
+                if (collect && in) {
+                    o.a[k] = (Real)tab[UAVSIM_SLOT_A * P + j];
+                    o.b[k] = (Real)tab[UAVSIM_SLOT_B * P + j];
+                    o.u[k] = (Real)tab[UAVSIM_SLOT_U * P + j];
+                }
+            }
         } else {
-            const Philox4 r = call(kStreamStep, j, 0);
-            box_muller<Real>(r.x, r.y, sigma, d, e);
-            put(UAVSIM_SLOT_D, j, d);
-            put(UAVSIM_SLOT_E, j, e);
+            const Philox4 q0 = call(lane, 0);
+            box_muller<Real>(q0.x, q0.y, sigma, o.d[0], o.e[0]);
+            if constexpr (SPL == 2) box_muller<Real>(q0.z, q0.w, sigma, o.d[1], o.e[1]);
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) o.a[k] = o.b[k] = o.u[k] = Real(0);
+            if (collect) {
+                if constexpr (SPL == 1) {
+                    box_muller<Real>(q0.z, q0.w, sigma, o.a[0], o.b[0]);
+                    const Philox4 q1 = call(lane, 1);
+                    o.u[0] = u01<Real>(q1.x);
+                } else {
+                    const Philox4 q1 = call(lane, 1);
+                    box_muller<Real>(q1.x, q1.y, sigma, o.a[0], o.b[0]);
+                    box_muller<Real>(q1.z, q1.w, sigma, o.a[1], o.b[1]);
+                    const Philox4 q2 = call(lane, 2);
+                    o.u[0] = u01<Real>(q2.x);
+                    o.u[1] = u01<Real>(q2.y);
+                }
+            }
+            if (exp) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const int j = lane + 32 * k;
+                    put(UAVSIM_SLOT_D, j, o.d[k]);
+                    put(UAVSIM_SLOT_E, j, o.e[k]);
+                    if (collect) {
+                        put(UAVSIM_SLOT_A, j, o.a[k]);
+                        put(UAVSIM_SLOT_B, j, o.b[k]);
+                        put(UAVSIM_SLOT_U, j, o.u[k]);
+                    }
+                }
+            }
         }
     }
-    // collect-step draws A (ADR), B (link probability), U (duty-cycle uniform): uav_env.py:535-551
-    __device__ __forceinline__ void collect_triple(int j, Real& a, Real& b, Real& u) const {
-        if constexpr (REPLAY) {
-            a = (Real)tab[UAVSIM_SLOT_A * P + j];
-            b = (Real)tab[UAVSIM_SLOT_B * P + j];
-            u = (Real)tab[UAVSIM_SLOT_U * P + j];
-        } else {
-            const Philox4 r = call(kStreamStep, j, 0);
-            box_muller<Real>(r.z, r.w, sigma, a, b);
-            const Philox4 q = call(kStreamStep, j, 1);
-            u = u01<Real>(q.x);
-            put(UAVSIM_SLOT_A, j, a);
-            put(UAVSIM_SLOT_B, j, b);
-            put(UAVSIM_SLOT_U, j, u);
-        }
-    }
-    // winner's range-check draw C: iot_sensors.py:131-133 via uav_env.py:581
-    __device__ __forceinline__ Real winner_draw(int j) const {
+    // winner's range-check draw C: iot_sensors.py:131-133 via uav_env.py:581 (called by the owner lane only)
+    __device__ __forceinline__ Real winner_draw(int lane, int k) const {
+        const int j = lane + 32 * k;
         if constexpr (REPLAY) {
             return (Real)tab[UAVSIM_SLOT_C * P + j];
         } else {
-            const Philox4 q = call(kStreamStep, j, 1);
+            const Philox4 q = call(lane, 4u + (uint32_t)k);
             Real c, unused;
-            box_muller<Real>(q.y, q.z, sigma, c, unused);
+            box_muller<Real>(q.x, q.y, sigma, c, unused);
             put(UAVSIM_SLOT_C, j, c);
             return c;
-        }
-    }
-    __device__ __forceinline__ void clear_export(int lane) const {
-        if (exp) {
-            const Real nan = Real(CUDART_NAN);
-            for (int i = lane; i < UAVSIM_NUM_SLOTS * P; i += 32) exp[i] = nan;
         }
     }
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-lane sensor registers
+// per-warp shared memory and per-lane sensor registers
 // ------------------------------------------------------------------------------------------------
+struct alignas(16) WarpSmem {
+    uavsim_env_record rec;           // this warp's environment record: one coalesced 128-byte load/store
+    double red[UAVSIM_MAX_SENSORS];  // parity-build ordered reductions; far-start candidate search
+    float obs[kMaxObsDim + 1];       // observation row staging
+};
+
+// Scalars every lane needs in registers during a step (the rest of the record stays in shared memory).
+struct Hot {
+    float x, y, elapsed, prev_dist;
+    double battery;
+    int W, H, N, step;
+    uint32_t vis_lo, vis_hi, episode;
+};
+
+__device__ __forceinline__ void load_record(WarpSmem& ws, const uavsim_env_record* g, int lane) {
+    __syncwarp();
+    reinterpret_cast<uint32_t*>(&ws.rec)[lane] = reinterpret_cast<const uint32_t*>(g)[lane];
+    __syncwarp();
+}
+__device__ __forceinline__ void store_record(const WarpSmem& ws, uavsim_env_record* g, int lane) {
+    __syncwarp();
+    reinterpret_cast<uint32_t*>(g)[lane] = reinterpret_cast<const uint32_t*>(&ws.rec)[lane];
+}
+__device__ __forceinline__ Hot read_hot(const uavsim_env_record& R) {
+    Hot h;
+    h.x = R.x;
+    h.y = R.y;
+    h.elapsed = R.elapsed_s;
+    h.prev_dist = R.prev_dist_nearest;
+    h.battery = R.battery;
+    h.W = R.grid_w;
+    h.H = R.grid_h;
+    h.N = R.num_sensors;
+    h.step = R.step;
+    h.vis_lo = R.visited_lo;
+    h.vis_hi = R.visited_hi;
+    h.episode = R.episode;
+    return h;
+}
+
 template <typename Real>
 struct Sensor {
     Real buf, tx, lost, ema, gen;  // gen: parity = total_data_generated; throughput = value at reset
@@ -398,11 +485,6 @@ __device__ __forceinline__ Real generated_of(const Params<Real>& p, const Sensor
         return fmaf(p.rate, elapsed, s.gen);  // total_data_generated = at_reset + rate * sum(dt)
 }
 
-struct Scratch {
-    float obs[kMaxObsDim + 1];
-    double red[UAVSIM_MAX_SENSORS];
-};
-
 template <typename Real, int SPL>
 __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real>& p, int e, int N, int lane,
                                              Sensor<Real> (&s)[SPL]) {
@@ -416,23 +498,28 @@ __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real
         s[k].attempt = false;
         s[k].det = Real(0);
         s[k].cur = Real(0);
+        // inactive lanes carry benign values and run the same arithmetic; they are masked at every
+        // reduction, ballot and store
+        SensorState<Real> v;
+        v.buf = v.tx = v.lost = Real(0);
+        v.ema = Real(CUDART_NAN);
+        float2 xy = make_float2(0.f, 0.f);
+        Real g = Real(0);
+        int sf = 12;
         if (s[k].active) {
-            const SensorState<Real> v = st[j];
-            const float2 xy = b.spos[row + j];
-            s[k].buf = v.buf;
-            s[k].tx = v.tx;
-            s[k].lost = v.lost;
-            s[k].ema = v.ema;
-            s[k].gen = gen[j];
-            s[k].sx = xy.x;
-            s[k].sy = xy.y;
-            s[k].sf = b.ssf[row + j];
-        } else {
-            s[k].buf = s[k].tx = s[k].lost = s[k].gen = Real(0);
-            s[k].ema = Real(CUDART_NAN);
-            s[k].sx = s[k].sy = 0.f;
-            s[k].sf = 12;
+            v = st[j];
+            xy = b.spos[row + j];
+            g = gen[j];
+            sf = b.ssf[row + j];
         }
+        s[k].buf = v.buf;
+        s[k].tx = v.tx;
+        s[k].lost = v.lost;
+        s[k].ema = v.ema;
+        s[k].gen = g;
+        s[k].sx = xy.x;
+        s[k].sy = xy.y;
+        s[k].sf = sf;
     }
 }
 
@@ -472,63 +559,64 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 }
 
 // UAVEnvironment._get_observation (uav_env.py:638-674) + zero padding to obs_slots (dqn.py:286-298).
-// Mutates EMA / SF (draw D) and draws E.  The row is staged in shared memory and written with
-// consecutive lanes on consecutive floats; ghost slots are zero-filled once when the buffer is
-// bound and never touched again (N is fixed per environment).
-template <typename Real, bool REPLAY, int SPL>
-__device__ __forceinline__ void observe(const Params<Real>& p, const uavsim_env_record& r, Sensor<Real> (&s)[SPL],
-                                        const Draws<Real, REPLAY>& dr, int lane, float* stage, float* out) {
-    const int N = r.num_sensors;
+// Mutates EMA / SF (draw D) and range-checks (draw E).  The row is staged in shared memory and written
+// with consecutive lanes on consecutive floats; ghost slots are zero-filled when the buffer is bound /
+// an episode starts and never touched by a step (N is fixed during an episode).
+template <typename Real, int SPL>
+__device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
+                                        const StepDraws<Real, SPL>& sd, int lane, float* stage, float* out) {
     __syncwarp();
+    float inv_w = 0.f, inv_h = 0.f;
+    if constexpr (!std::is_same<Real, double>::value) {
+        inv_w = __frcp_rn((float)h.W);
+        inv_h = __frcp_rn((float)h.H);
+    }
     if (lane == 0) {
         if constexpr (std::is_same<Real, double>::value) {
-            stage[0] = (float)((double)r.x / (double)r.grid_w);
-            stage[1] = (float)((double)r.y / (double)r.grid_h);
-            stage[2] = (float)(r.battery / p.max_battery);
+            stage[0] = (float)((double)h.x / (double)h.W);
+            stage[1] = (float)((double)h.y / (double)h.H);
+            stage[2] = (float)(h.battery / p.max_battery);
         } else {
-            stage[0] = r.x / (float)r.grid_w;
-            stage[1] = r.y / (float)r.grid_h;
-            stage[2] = (float)r.battery / (float)p.max_battery;
+            stage[0] = h.x * inv_w;
+            stage[1] = h.y * inv_h;
+            stage[2] = (float)h.battery * p.inv_max_battery;
         }
     }
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
+        const Real urg = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], h.elapsed));
+        adr_update(p, s[k].det + sd.d[k], s[k].ema, s[k].sf);
+        const bool in_range = (s[k].det + sd.e[k]) >= p.thr;
         if (s[k].active) {
-            const Real urg = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], r.elapsed_s));
-            Real d, e;
-            dr.obs_pair(j, d, e);
-            adr_update(p, s[k].det + d, s[k].ema, s[k].sf);
-            const bool in_range = (s[k].det + e) >= p.thr;
             float* o = stage + 3 + p.fps * j;
-            o[0] = (float)(s[k].buf / p.maxbuf);
+            o[0] = (float)fdiv(s[k].buf, p.maxbuf);
             o[1] = (float)urg;
-            o[2] = in_range ? link_quality_of(s[k].sf) : 0.0f;
+            o[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
             if (p.fps == 5) {  // include_sensor_positions, uav_env.py:668-672
                 if constexpr (std::is_same<Real, double>::value) {
-                    o[3] = (float)(((double)s[k].sx - (double)r.x) / (double)r.grid_w);
-                    o[4] = (float)(((double)s[k].sy - (double)r.y) / (double)r.grid_h);
+                    o[3] = (float)(((double)s[k].sx - (double)h.x) / (double)h.W);
+                    o[4] = (float)(((double)s[k].sy - (double)h.y) / (double)h.H);
                 } else {
-                    o[3] = (s[k].sx - r.x) / (float)r.grid_w;
-                    o[4] = (s[k].sy - r.y) / (float)r.grid_h;
+                    o[3] = (s[k].sx - h.x) * inv_w;
+                    o[4] = (s[k].sy - h.y) * inv_h;
                 }
             }
         }
     }
     __syncwarp();
-    const int n = 3 + p.fps * N;
+    const int n = 3 + p.fps * h.N;
     for (int i = lane; i < n; i += 32) out[i] = stage[i];
-    __syncwarp();
 }
 
 // DomainRandEnv._dist_to_nearest_with_data (dqn.py:405-412): float32 norm, min over sensors with data.
 template <typename Real, int SPL>
-__device__ __forceinline__ float nearest_with_data(const uavsim_env_record& r, const Sensor<Real> (&s)[SPL]) {
+__device__ __forceinline__ float nearest_with_data(float x, float y, const Sensor<Real> (&s)[SPL]) {
     float best = CUDART_INF_F;
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         if (s[k].active && s[k].buf > Real(0)) {
-            const float dx = s[k].sx - r.x, dy = s[k].sy - r.y;
+            const float dx = s[k].sx - x, dy = s[k].sy - y;
             best = fminf(best, sqrtf(dx * dx + dy * dy));
         }
     }
@@ -537,25 +625,25 @@ __device__ __forceinline__ float nearest_with_data(const uavsim_env_record& r, c
 }
 
 template <typename Real, int SPL>
-__device__ __forceinline__ void compute_det(const Params<Real>& p, const uavsim_env_record& r, Sensor<Real> (&s)[SPL]) {
+__device__ __forceinline__ void compute_det(const Params<Real>& p, float x, float y, Sensor<Real> (&s)[SPL]) {
 #pragma unroll
-    for (int k = 0; k < SPL; ++k)
-        if (s[k].active) s[k].det = det_rssi(p, r.x, r.y, s[k].sx, s[k].sy);
+    for (int k = 0; k < SPL; ++k) s[k].det = det_rssi(p, x, y, s[k].sx, s[k].sy);
 }
 
 // ------------------------------------------------------------------------------------------------
-// reset
+// episode end / reset
 // ------------------------------------------------------------------------------------------------
 // Episode statistics written when an environment finishes: DomainRandEnv.last_episode_stats
-// (dqn.py:305-331) + what Monitor reports.  Rare path: plain float64 shuffle reductions.
+// (dqn.py:305-331) + what Monitor reports.  Rare path: plain float64 shuffle reductions.  R is the
+// committed record in shared memory.
 template <typename Real, int SPL>
 __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const Buffers& b, int e, int lane,
-                                                    const uavsim_env_record& r, const Sensor<Real> (&s)[SPL]) {
+                                                    const uavsim_env_record& R, const Sensor<Real> (&s)[SPL]) {
     double g = 0, t = 0, l = 0, s1 = 0, s2 = 0, cnt = 0;
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         if (s[k].active) {
-            const double gen = (double)generated_of(p, s[k], r.elapsed_s);
+            const double gen = (double)generated_of(p, s[k], R.elapsed_s);
             g += gen;
             t += (double)s[k].tx;
             l += (double)s[k].lost;
@@ -574,32 +662,32 @@ __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const
     s2 = warp_sum(s2);
     cnt = warp_sum(cnt);
     if (lane == 0) {
-        const int N = r.num_sensors;
-        const int nv = __popc(r.visited_lo) + __popc(r.visited_hi);
-        const double used = p.max_battery - r.battery;
+        const int N = R.num_sensors;
+        const int nv = __popc(R.visited_lo) + __popc(R.visited_hi);
+        const double used = p.max_battery - R.battery;
         const double mean = cnt > 0 ? s1 / cnt : 0.0;
         const double var = cnt > 0 ? fmax(s2 / cnt - mean * mean, 0.0) : 0.0;
         double v[UAVSIM_STAT_COUNT];
-        v[UAVSIM_STAT_RETURN] = r.episode_return;
-        v[UAVSIM_STAT_LENGTH] = r.step;
+        v[UAVSIM_STAT_RETURN] = R.episode_return;
+        v[UAVSIM_STAT_LENGTH] = R.step;
         v[UAVSIM_STAT_TOTAL_GENERATED] = g;
         v[UAVSIM_STAT_TOTAL_COLLECTED] = t;
         v[UAVSIM_STAT_TOTAL_LOST] = l;
-        v[UAVSIM_STAT_BATTERY_REMAINING] = r.battery;
+        v[UAVSIM_STAT_BATTERY_REMAINING] = R.battery;
         v[UAVSIM_STAT_NDR] = (double)nv / N * 100;
         v[UAVSIM_STAT_FAIRNESS_STD] = sqrt(var);
         v[UAVSIM_STAT_JAINS] = (cnt > 0 && s2 > 0) ? (s1 * s1) / (cnt * s2) : 1.0;  // dqn.py:446-451
-        v[UAVSIM_STAT_GRID_W] = r.grid_w;
-        v[UAVSIM_STAT_GRID_H] = r.grid_h;
+        v[UAVSIM_STAT_GRID_W] = R.grid_w;
+        v[UAVSIM_STAT_GRID_H] = R.grid_h;
         v[UAVSIM_STAT_NUM_SENSORS] = N;
         v[UAVSIM_STAT_DATA_EFFICIENCY] = g > 0 ? t / g * 100 : 0.0;
         v[UAVSIM_STAT_BYTES_PER_WH] = used > 0 ? t / used : 0.0;
-        v[UAVSIM_STAT_TIME_TO_COVERAGE] = r.first_full_coverage_step;
-        v[UAVSIM_STAT_CAPTURE_TRIGGERS] = r.capture_triggers;
-        v[UAVSIM_STAT_BOUNDARY_HITS] = r.boundary_hits;
-        v[UAVSIM_STAT_EDGE_STEPS] = r.edge_steps;
-        v[UAVSIM_STAT_COLLISIONS] = r.collisions;
-        v[UAVSIM_STAT_BASE_RETURN] = r.total_reward;
+        v[UAVSIM_STAT_TIME_TO_COVERAGE] = R.first_full_coverage_step;
+        v[UAVSIM_STAT_CAPTURE_TRIGGERS] = R.capture_triggers;
+        v[UAVSIM_STAT_BOUNDARY_HITS] = R.boundary_hits;
+        v[UAVSIM_STAT_EDGE_STEPS] = R.edge_steps;
+        v[UAVSIM_STAT_COLLISIONS] = R.collisions;
+        v[UAVSIM_STAT_BASE_RETURN] = R.total_reward;
         if (b.episode_stats)
             for (int i = 0; i < UAVSIM_STAT_COUNT; ++i) b.episode_stats[(size_t)e * UAVSIM_STAT_COUNT + i] = v[i];
         if (b.stat_sums) {
@@ -609,36 +697,39 @@ __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const
     }
 }
 
-// Start a new episode for this warp's environment (state in registers), then write its first
-// observation.  FIXED: UAVEnvironment.reset (uav_env.py:400-427, iot_sensors.py:305-321).
-// DOMAIN_RAND: DomainRandEnv.reset (dqn.py:301-372).  `r.episode` already names the NEW episode.
+// Start a new episode for this warp's environment: record in shared memory (ws.rec), sensors in
+// registers; writes the first observation.  FIXED: UAVEnvironment.reset (uav_env.py:400-427,
+// iot_sensors.py:305-321).  DOMAIN_RAND: DomainRandEnv.reset (dqn.py:301-372).  ws.rec.episode names
+// the NEW episode on entry and is incremented on exit.
 template <typename Real, bool REPLAY, int SPL>
-__device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& b, int e, int lane, uavsim_env_record& r,
-                                          Sensor<Real> (&s)[SPL], Scratch& sc, bool& layout_changed, Real* exp) {
+__device__ __noinline__ void reset_env(const Params<Real>& p, const Buffers& b, int e, int lane, WarpSmem& ws,
+                                       Sensor<Real> (&s)[SPL], Real* exp) {
+    uavsim_env_record& R = ws.rec;
+    __syncwarp();
     const uint64_t gid = (uint64_t)(p.env_id_offset + e);
     const uint32_t env_lo = (uint32_t)gid, env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
+    const uint32_t episode = R.episode;
     int init_sf = p.init_sf;
-    layout_changed = false;
+    int W = R.grid_w, H = R.grid_h, N = R.num_sensors;
+    float start_x = R.start_x, start_y = R.start_y;
 
     if (p.domain_rand) {
-        layout_changed = true;
         if constexpr (REPLAY) {
             // injected scenario (the reference draws it from unseeded / global generators)
             if (b.reset_init_sf) init_sf = b.reset_init_sf[e];
             if (b.rs_grid_wh) {
-                r.grid_w = b.rs_grid_wh[2 * e];
-                r.grid_h = b.rs_grid_wh[2 * e + 1];
+                W = b.rs_grid_wh[2 * e];
+                H = b.rs_grid_wh[2 * e + 1];
             }
-            if (b.rs_num_sensors) r.num_sensors = b.rs_num_sensors[e];
+            if (b.rs_num_sensors) N = b.rs_num_sensors[e];
             if (b.rs_start_xy) {
-                r.start_x = b.rs_start_xy[2 * e];
-                r.start_y = b.rs_start_xy[2 * e + 1];
+                start_x = b.rs_start_xy[2 * e];
+                start_y = b.rs_start_xy[2 * e + 1];
             }
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 const int j = lane + 32 * k;
-                s[k].active = j < r.num_sensors;
-                if (s[k].active && b.rs_sensor_xy) {
+                if (j < N && b.rs_sensor_xy) {
                     s[k].sx = b.rs_sensor_xy[((size_t)e * p.P + j) * 2];
                     s[k].sy = b.rs_sensor_xy[((size_t)e * p.P + j) * 2 + 1];
                 }
@@ -648,8 +739,8 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
             //     OLD start position (dqn.py:338-353 with uav_env.py:407-427): one ADR update from None.
             {
                 const float s0x = shfl(s[0].sx, 0), s0y = shfl(s[0].sy, 0);
-                const Real det0 = det_rssi(p, r.start_x, r.start_y, s0x, s0y);
-                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), r.episode, 1, p.key0, p.key1);
+                const Real det0 = det_rssi(p, start_x, start_y, s0x, s0y);
+                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), episode, 1, p.key0, p.key1);
                 Real z0, z1;
                 box_muller<Real>(q.x, q.y, p.sigma, z0, z1);
                 Real ema = Real(CUDART_NAN);
@@ -657,41 +748,40 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                 adr_update(p, det0 + z0, ema, sf);
                 init_sf = sf;
                 // (b) grid from the current curriculum stage (dqn.py:280-283)
-                const Philox4 g = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), r.episode, 0, p.key0, p.key1);
+                const Philox4 g = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), episode, 0, p.key0, p.key1);
                 const int gi = (int)(g.x % (uint32_t)p.num_grids);
-                r.grid_w = p.grids[gi][0];
-                r.grid_h = p.grids[gi][1];
+                W = p.grids[gi][0];
+                H = p.grids[gi][1];
             }
             // (c) uniform layout (dqn.py:342-343, _layout_uniform :135-137)
-            const double W = (double)r.grid_w, H = (double)r.grid_h;
+            const double Wd = (double)W, Hd = (double)H;
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 const int j = lane + 32 * k;
-                s[k].active = j < r.num_sensors;
-                if (s[k].active) {
-                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamLayout << 24), r.episode, (uint32_t)j, p.key0,
+                if (j < N) {
+                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamLayout << 24), episode, (uint32_t)j, p.key0,
                                                     p.key1);
-                    s[k].sx = (float)(u01<double>(q.x) * W);
-                    s[k].sy = (float)(u01<double>(q.y) * H);
+                    s[k].sx = (float)(u01<double>(q.x) * Wd);
+                    s[k].sy = (float)(u01<double>(q.y) * Hd);
                 }
             }
             // (d) far start: first candidate >= min_start_dist from every sensor, else the furthest of
             //     max_start_tries (dqn.py:375-403).  32 candidates per round, one per lane.
-            float2* pos = reinterpret_cast<float2*>(sc.red);  // 64 float2 = 512 B
+            float2* pos = reinterpret_cast<float2*>(ws.red);  // 64 float2 = 512 B
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < SPL; ++k)
-                if (s[k].active) pos[lane + 32 * k] = make_float2(s[k].sx, s[k].sy);
+                if (lane + 32 * k < N) pos[lane + 32 * k] = make_float2(s[k].sx, s[k].sy);
             __syncwarp();
             float best_d = -1.0f, best_x = 0.f, best_y = 0.f;
             bool found = false;
             for (int base = 0; base < p.max_start_tries && !found; base += 32) {
                 const int t = base + lane;
-                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamStart << 24), r.episode, (uint32_t)t, p.key0, p.key1);
-                const float cx = (float)(0.05 * W + (0.95 * W - 0.05 * W) * u01<double>(q.x));
-                const float cy = (float)(0.05 * H + (0.95 * H - 0.05 * H) * u01<double>(q.y));
+                const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamStart << 24), episode, (uint32_t)t, p.key0, p.key1);
+                const float cx = (float)(0.05 * Wd + (0.95 * Wd - 0.05 * Wd) * u01<double>(q.x));
+                const float cy = (float)(0.05 * Hd + (0.95 * Hd - 0.05 * Hd) * u01<double>(q.y));
                 float dmin = CUDART_INF_F;
-                for (int i = 0; i < r.num_sensors; ++i) {
+                for (int i = 0; i < N; ++i) {
                     const float dx = cx - pos[i].x, dy = cy - pos[i].y;
                     dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
                 }
@@ -704,10 +794,10 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                     found = true;
                 } else {
                     // running "furthest so far", first occurrence wins ties (strict > at dqn.py:397)
-                    float d = valid ? dmin : -2.0f;
+                    const float d = valid ? dmin : -2.0f;
                     const float m = warp_max(d);
+                    const unsigned who = __ballot_sync(kFull, d == m);
                     if (m > best_d) {
-                        const unsigned who = __ballot_sync(kFull, d == m);
                         const int src = __ffs(who) - 1;
                         best_d = m;
                         best_x = shfl(cx, src);
@@ -716,30 +806,18 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                 }
             }
             __syncwarp();
-            r.start_x = best_x;
-            r.start_y = best_y;
+            start_x = best_x;
+            start_y = best_y;
         }
     }
-
-    // UAV.reset (uav.py:241-258) and the episode counters (uav_env.py:412-424)
-    r.x = r.start_x;
-    r.y = r.start_y;
-    r.battery = p.max_battery;
-    r.total_reward = 0.0;
-    r.total_data_collected = 0.0;
-    r.episode_return = 0.0;
-    r.last_step_bytes = 0.f;
-    r.elapsed_s = 0.f;
-    r.step = 0;
-    r.visited_lo = r.visited_hi = 0u;
-    r.capture_triggers = r.boundary_hits = r.edge_steps = r.collisions = r.delivered = 0;
-    r.first_full_coverage_step = -1;
 
     // IoTSensor.reset (iot_sensors.py:305-321) / fresh IoTSensor objects (dqn.py:345-360)
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
-        s[k].active = j < r.num_sensors;
+        s[k].active = j < N;
+        s[k].attempt = false;
+        s[k].cur = Real(0);
         if (s[k].active) {
             if (p.domain_rand) {
                 s[k].buf = Real(0);
@@ -748,7 +826,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                 if constexpr (REPLAY) {
                     fill = (Real)b.reset_fill[(size_t)e * p.P + j];
                 } else {
-                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamFill << 24), r.episode, (uint32_t)j, p.key0,
+                    const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamFill << 24), episode, (uint32_t)j, p.key0,
                                                     p.key1);
                     fill = Real(0.20) + (Real(0.60) - Real(0.20)) * u01<Real>(q.x);  // np_random.uniform(0.20, 0.60)
                 }
@@ -760,53 +838,98 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
             s[k].lost = Real(0);
             s[k].ema = Real(CUDART_NAN);
             s[k].sf = init_sf;
-            if (exp) exp[UAVSIM_SLOT_U * p.P + j] = s[k].buf / p.maxbuf;  // the fill actually used (diagnostic)
+            if (exp) exp[UAVSIM_SLOT_U * p.P + j] = fdiv(s[k].buf, p.maxbuf);  // the fill actually used (diagnostic)
+        } else {
+            s[k].buf = s[k].tx = s[k].lost = s[k].gen = Real(0);
+            s[k].ema = Real(CUDART_NAN);
+            s[k].sx = s[k].sy = 0.f;
+            s[k].sf = 12;
         }
     }
-    r.reserved[0] = init_sf;
-    compute_det(p, r, s);
-    Draws<Real, REPLAY> dr;
+
+    // UAV.reset (uav.py:241-258) and the episode counters (uav_env.py:412-424)
+    Hot h;
+    h.x = start_x;
+    h.y = start_y;
+    h.elapsed = 0.f;
+    h.battery = p.max_battery;
+    h.W = W;
+    h.H = H;
+    h.N = N;
+    h.step = 0;
+    h.vis_lo = h.vis_hi = 0u;
+    h.episode = episode;
+    compute_det(p, h.x, h.y, s);
+    Draws<Real, REPLAY, SPL> dr;
     dr.P = p.P;
     dr.sigma = p.sigma;
     dr.k0 = p.key0;
     dr.k1 = p.key1;
     dr.env_lo = env_lo;
     dr.env_hi = env_hi;
-    dr.episode = r.episode;
+    dr.episode = episode;
     dr.step = 0;
     dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = exp;
+    StepDraws<Real, SPL> sd;
+    dr.generate(lane, false, sd);
     float* out = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, REPLAY, SPL>(p, r, s, dr, lane, sc.obs, out);
-    for (int i = 3 + p.fps * r.num_sensors + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
-    r.prev_dist_nearest = p.domain_rand ? nearest_with_data(r, s) : 0.f;
-    if (b.action_mask && lane == 0) b.action_mask[e] = action_mask_of(r.x, r.y, r.grid_w, r.grid_h);
+    observe<Real, SPL>(p, h, s, sd, lane, ws.obs, out);
+    for (int i = 3 + p.fps * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
+    const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
+    __syncwarp();
+    if (lane == 0) {
+        R.x = h.x;
+        R.y = h.y;
+        R.start_x = start_x;
+        R.start_y = start_y;
+        R.battery = p.max_battery;
+        R.total_reward = 0.0;
+        R.total_data_collected = 0.0;
+        R.episode_return = 0.0;
+        R.last_step_bytes = 0.f;
+        R.prev_dist_nearest = prev;
+        R.elapsed_s = 0.f;
+        R.step = 0;
+        R.grid_w = W;
+        R.grid_h = H;
+        R.num_sensors = N;
+        R.visited_lo = R.visited_hi = 0u;
+        R.capture_triggers = R.boundary_hits = R.edge_steps = R.collisions = R.delivered = 0;
+        R.first_full_coverage_step = -1;
+        R.episode = episode + 1;
+        R.reserved[0] = init_sf;
+        if (b.action_mask) b.action_mask[e] = action_mask_of(h.x, h.y, W, H);
+    }
+    __syncwarp();
+}
+
+template <typename Real>
+constexpr int min_blocks_per_sm() {
+    return std::is_same<Real, double>::value ? 1 : 3;
 }
 
 template <typename Real, bool REPLAY, int SPL>
-__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ Params<Real> p,
-                                                         const __grid_constant__ Buffers b, const uint8_t* mask) {
-    __shared__ Scratch scratch[kWarpsPerBlock];
+__global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
+    reset_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b, const uint8_t* mask) {
+    __shared__ WarpSmem smem[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= b.E) return;
-    if (mask && !mask[e]) return;
-    uavsim_env_record r = b.rec[e];
-    Sensor<Real> s[SPL];
-    load_sensors<Real, SPL>(b, p, e, r.num_sensors, lane, s);
-    bool layout_changed;
-    Real* exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-    if (exp) {
-        const Real nan = Real(CUDART_NAN);
-        for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
-        __syncwarp();
-    }
-    reset_env<Real, REPLAY, SPL>(p, b, e, lane, r, s, scratch[warp], layout_changed, exp);
-    r.episode += 1;  // the next reset (in-step or explicit) starts a new counter block
-    store_sensors<Real, SPL>(b, p, e, lane, s, true);
-    if (lane == 0) {
-        b.rec[e] = r;
-        if (b.done) b.done[e] = 0;
+    WarpSmem& ws = smem[warp];
+    for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
+        if (mask && !mask[e]) continue;
+        load_record(ws, b.rec + e, lane);
+        Sensor<Real> s[SPL];
+        load_sensors<Real, SPL>(b, p, e, ws.rec.num_sensors, lane, s);
+        Real* exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+        if (exp) {
+            const Real nan = Real(CUDART_NAN);
+            for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
+            __syncwarp();
+        }
+        reset_env<Real, REPLAY, SPL>(p, b, e, lane, ws, s, exp);
+        store_sensors<Real, SPL>(b, p, e, lane, s, true);
+        store_record(ws, b.rec + e, lane);
+        if (lane == 0 && b.done) b.done[e] = 0;
     }
 }
 
@@ -830,394 +953,435 @@ __device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& i
     imax = idx;
 }
 
+// What a COLLECT step hands back to the common tail of the step.
+template <typename Real>
+struct CollectOut {
+    Real reward, total_bytes, urg_red, mean_urg;
+    int collisions, captures, delivered;
+    bool any_new, was_empty, all_collected;
+    unsigned long long att_mask, win_mask;
+};
+
+// UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment.
 template <typename Real, bool REPLAY, int SPL>
-__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ Params<Real> p,
-                                                        const __grid_constant__ Buffers b, const int32_t* __restrict__ actions) {
-    __shared__ Scratch scratch[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= b.E) return;
-    Scratch& sc = scratch[warp];
+__device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Sensor<Real> (&s)[SPL],
+                                               const StepDraws<Real, SPL>& sd, const Draws<Real, REPLAY, SPL>& dr,
+                                               Real step_loss, int lane, WarpSmem& ws, CollectOut<Real>& out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
-
-    const int action = actions[e];
-    if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
-        if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
-        return;
-    }
-    uavsim_env_record r = b.rec[e];
-    const int N = r.num_sensors;
-    Sensor<Real> s[SPL];
-    load_sensors<Real, SPL>(b, p, e, N, lane, s);
-
-    const uint64_t gid = (uint64_t)(p.env_id_offset + e);
-    Draws<Real, REPLAY> dr;
-    dr.P = p.P;
-    dr.sigma = p.sigma;
-    dr.k0 = p.key0;
-    dr.k1 = p.key1;
-    dr.env_lo = (uint32_t)gid;
-    dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
-    dr.episode = r.episode - 1;  // r.episode counts resets done; the running episode is one less
-    dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-    dr.exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-    if (!REPLAY) dr.clear_export(lane);
-
-    const float prev_dist = r.prev_dist_nearest;
-
-    // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
-    r.step += 1;
-    dr.step = (uint32_t)r.step;
-    {
-        const double W = r.grid_w, H = r.grid_h, ux = r.x, uy = r.y, eps = 1e-6;
-        if (ux <= eps || uy <= eps || ux >= W - 1 - eps || uy >= H - 1 - eps) r.edge_steps += 1;
-    }
-    const bool collect = action == 4;
-    const Real dt = collect ? p.cd : Real(1);
-    r.elapsed_s += (float)dt;
-
-    // ---- iot_sensors.py:114-125: age the buffers ----
-    Real loss[SPL];
+    const int N = h.N;
+    float before[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) before[k] = (float)fdiv(s[k].buf, p.rate);  // _get_sensor_urgencies, :386-394
+    h.battery -= p.e_hover;                                                    // uav.py:205
+    const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
+    // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
+    unsigned att[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
-        loss[k] = Real(0);
-        if (s[k].active) {
-            const Real nw = p.rate * dt;
-            if constexpr (kParity) s[k].gen += nw;
-            const Real pot = s[k].buf + nw;
-            if (pot > p.maxbuf) {
-                loss[k] = pot - p.maxbuf;
-                s[k].buf = p.maxbuf;
-                s[k].lost += loss[k];
+        bool a = false;
+        if (s[k].active && s[k].buf > Real(0)) {
+            s[k].cur = s[k].det + sd.a[k];
+            adr_update(p, s[k].cur, s[k].ema, s[k].sf);
+            const Real rb = s[k].det + sd.b[k];
+            Real plink;
+            if (rb < p.thr) {
+                plink = Real(0);
             } else {
-                s[k].buf = pot;
+                const Real x = (rb - p.noise_floor) - required_snr_of<Real>(s[k].sf);
+                if constexpr (kParity)
+                    plink = 1.0 / (1.0 + exp(-x));
+                else
+                    plink = __fdividef(1.0f, 1.0f + __expf(-x));
+            }
+            a = (plink * p.duty_frac) > sd.u[k];
+        }
+        s[k].attempt = a;
+        att[k] = __ballot_sync(kFull, a);
+    }
+    unsigned long long att_mask = (unsigned long long)att[0];
+    if (SPL > 1) att_mask |= (unsigned long long)att[SPL - 1] << 32;
+
+    // Phase 3+4: SF groups in first-appearance order; k==1 wins, k>1 collides unless the strongest beats
+    // the runner-up by the capture threshold; each winner is range-checked (draw C) and drained.
+    Real total_bytes = Real(0), urg_acc = Real(0);
+    int nwin = 0, collisions = 0, captures = 0, delivered = 0;
+    bool any_new = false;
+    unsigned long long win_mask = 0ull, remaining = att_mask;
+    while (remaining) {
+        const int i0 = __ffsll((long long)remaining) - 1;
+        bool sel[SPL];
+        unsigned long long gm = 0ull;
+        int sf0 = 0;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int v = shfl(s[k].sf, i0 & 31);
+            if ((i0 >> 5) == k) sf0 = v;
+        }
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            sel[k] = s[k].attempt && s[k].sf == sf0;
+            gm |= (unsigned long long)__ballot_sync(kFull, sel[k]) << (32 * k);
+        }
+        remaining &= ~gm;
+        const int cnt = __popcll(gm);
+        int winner = -1;
+        if (cnt == 1) {
+            winner = i0;
+        } else {
+            collisions += cnt - 1;
+            Real v1 = Real(0);
+            int i1 = -1;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                if (sel[k] && (i1 < 0 || s[k].cur > v1)) {
+                    v1 = s[k].cur;
+                    i1 = lane + 32 * k;
+                }
+            }
+            Real top_v, sec_v;
+            int top_i, sec_i;
+            group_argmax(v1, i1, top_v, top_i);
+            Real v2 = Real(0);
+            int i2 = -1;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                if (sel[k] && j != top_i && (i2 < 0 || s[k].cur > v2)) {
+                    v2 = s[k].cur;
+                    i2 = j;
+                }
+            }
+            group_argmax(v2, i2, sec_v, sec_i);
+            if (top_v > (sec_v + p.capture_db)) {  // uav_env.py:569
+                winner = top_i;
+                captures += 1;
+            }
+        }
+        if (winner >= 0) {
+            win_mask |= 1ull << winner;
+            // the owner lane performs IoTSensor.collect_data (iot_sensors.py:127-145)
+            Real got = Real(0), urg_w = Real(0);
+            int in_range = 0;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                if (lane + 32 * k == winner) {
+                    const Real rc = s[k].det + dr.winner_draw(lane, k);
+                    in_range = rc >= p.thr;
+                    if (in_range && s[k].buf > Real(0)) {
+                        const Real cap = data_rate_of<Real>(s[k].sf) * p.cd;
+                        got = s[k].buf < cap ? s[k].buf : cap;
+                        s[k].buf -= got;
+                        s[k].tx += got;
+                    }
+                    urg_w = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], h.elapsed));
+                }
+            }
+            const int owner = winner & 31;
+            got = shfl(got, owner);
+            urg_w = shfl(urg_w, owner);
+            in_range = shfl(in_range, owner);
+            urg_acc += urg_w;  // np.mean over <= 6 winners adds left to right (uav_env.py:610-615)
+            nwin += 1;
+            if (in_range && got > Real(0)) {
+                total_bytes += got;
+                delivered += 1;
+                const bool seen = winner < 32 ? (h.vis_lo >> winner) & 1u : (h.vis_hi >> (winner - 32)) & 1u;
+                if (!seen) {
+                    any_new = true;
+                    if (winner < 32)
+                        h.vis_lo |= 1u << winner;
+                    else
+                        h.vis_hi |= 1u << (winner - 32);
+                }
             }
         }
     }
-    const Real step_loss = sensor_sum<Real, SPL>(loss, N, lane, sc.red, kSumSequential);
-
-    Real reward;
-    int collisions = 0;
-    Real total_bytes = Real(0), urg_red = Real(0), mean_urg = Real(0);
-    bool any_new = false, was_empty = false, all_collected = false;
-    unsigned long long att_mask = 0ull, win_mask = 0ull;
-
-    if (!collect) {
-        // ---- uav.py:127-185 + reward_function.py:69-79 + uav_env.py:494-516 ----
-        r.last_step_bytes = 0.f;
-        float nx = r.x, ny = r.y;
-        if (action == 0)
-            ny += 1.0f;
-        else if (action == 1)
-            ny -= 1.0f;
-        else if (action == 2)
-            nx -= 1.0f;
-        else
-            nx += 1.0f;
-        const double before = r.battery;
-        const bool ok = (0.f <= nx) && (nx < (float)r.grid_w) && (0.f <= ny) && (ny < (float)r.grid_h);
-        if (ok) {
-            r.x = nx;
-            r.y = ny;
-            r.battery -= p.e_move;
-        } else {
-            r.battery -= p.e_fail;
-            r.boundary_hits += 1;
-        }
-        const Real used = (Real)(before - r.battery);
-        reward = p.p_step;
-        reward += ok ? p.r_move : p.p_boundary;
-        reward += p.p_battery * used;
-        reward += p.p_data_loss * step_loss;
-        compute_det(p, r, s);  // for the observation at the new position
-    } else {
-        // ---- uav_env.py:518-632 ----
-        float before[SPL];
+    // Phase 5: fairness metrics (uav_env.py:596-604)
+    unsigned empty_b = 0u, nonempty_b = 0u;
+    float diff[SPL];
 #pragma unroll
-        for (int k = 0; k < SPL; ++k) before[k] = s[k].active ? (float)(s[k].buf / p.rate) : 0.f;  // :386-394
-        r.battery -= p.e_hover;
-        const Real used = (Real)p.used_hover;
-        compute_det(p, r, s);
-        // Phase 2: ADR update, link probability, duty-cycle gate
-        unsigned att[SPL];
+    for (int k = 0; k < SPL; ++k) {
+        empty_b |= __ballot_sync(kFull, s[k].active && s[k].buf <= Real(0));
+        nonempty_b |= __ballot_sync(kFull, s[k].active && !(s[k].buf <= Real(0)));
+        const float d = before[k] - (float)fdiv(s[k].buf, p.rate);
+        diff[k] = d > 0.f ? d : 0.f;
+    }
+    const bool was_empty = empty_b != 0u, all_collected = nonempty_b == 0u;
+    const Real urg_red = (Real)sensor_sum<Real, SPL>(diff, N, lane, ws.red, kSumNumpy);  // float32 np.sum
+    const Real mean_urg = nwin > 0 ? fdiv(urg_acc, (Real)nwin) : Real(0);
+    // Phase 6: reward_function.py:81-128, same order of additions
+    Real reward = p.p_step + p.p_hover;
+    if (total_bytes > Real(0)) {
+        reward += p.r_per_byte * total_bytes * mean_urg;
+        if (any_new) reward += p.r_new;
+    }
+    if (urg_red > Real(0)) reward += p.r_urg_red * urg_red;
+    if (was_empty && total_bytes == Real(0)) reward += p.p_revisit;
+    reward += p.p_battery * used;
+    if (collisions > 0) reward += p.p_collision * (Real)collisions;
+    if (step_loss > Real(0)) reward += p.p_data_loss * step_loss;
+    if (N > 1) {  // calculate_starvation_penalty, reward_function.py:46-57
+        Real mx = Real(0);
 #pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            const int j = lane + 32 * k;
-            bool a = false;
-            if (s[k].active && s[k].buf > Real(0)) {
-                Real da, db, u;
-                dr.collect_triple(j, da, db, u);
-                s[k].cur = s[k].det + da;
-                adr_update(p, s[k].cur, s[k].ema, s[k].sf);
-                const Real rb = s[k].det + db;
-                Real plink;
-                if (rb < p.thr) {
-                    plink = Real(0);
-                } else {
-                    const Real x = (rb - p.noise_floor) - (Real)required_snr_of(s[k].sf);
-                    if constexpr (kParity)
-                        plink = 1.0 / (1.0 + exp(-x));
-                    else
-                        plink = __fdividef(1.0f, 1.0f + __expf(-x));
-                }
-                a = (plink * p.duty_frac) > u;
-            }
-            s[k].attempt = a;
-            att[k] = __ballot_sync(kFull, a);
-        }
-        att_mask = (unsigned long long)att[0];
-        if (SPL > 1) att_mask |= (unsigned long long)att[SPL - 1] << 32;
-
-        // Phase 3+4: SF groups in first-appearance order; k==1 wins, k>1 collides unless the strongest
-        // beats the runner-up by the capture threshold; each winner is range-checked (draw C) and drained.
-        Real urg_list[6];
-        int nwin = 0;
-        unsigned long long remaining = att_mask;
-        while (remaining) {
-            const int i0 = __ffsll((long long)remaining) - 1;
-            int sf_sel[SPL];
-            unsigned long long gm = 0ull;
-            int sf0 = 0;
-#pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                const int v = shfl(s[k].sf, i0 & 31);
-                if ((i0 >> 5) == k) sf0 = v;
-            }
-#pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                sf_sel[k] = s[k].attempt && s[k].sf == sf0;
-                gm |= (unsigned long long)__ballot_sync(kFull, sf_sel[k]) << (32 * k);
-            }
-            remaining &= ~gm;
-            const int cnt = __popcll(gm);
-            int winner = -1;
-            if (cnt == 1) {
-                winner = i0;
-            } else {
-                collisions += cnt - 1;
-                // strongest and runner-up by current_rssi (draw A)
-                Real v1 = Real(0);
-                int i1 = -1;
-#pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    if (sf_sel[k] && (i1 < 0 || s[k].cur > v1)) {
-                        v1 = s[k].cur;
-                        i1 = lane + 32 * k;
-                    }
-                }
-                Real top_v;
-                int top_i;
-                group_argmax(v1, i1, top_v, top_i);
-                Real v2 = Real(0);
-                int i2 = -1;
-#pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    const int j = lane + 32 * k;
-                    if (sf_sel[k] && j != top_i && (i2 < 0 || s[k].cur > v2)) {
-                        v2 = s[k].cur;
-                        i2 = j;
-                    }
-                }
-                Real sec_v;
-                int sec_i;
-                group_argmax(v2, i2, sec_v, sec_i);
-                if (top_v > (sec_v + p.capture_db)) {
-                    winner = top_i;
-                    r.capture_triggers += 1;
-                }
-            }
-            if (winner >= 0) {
-                win_mask |= 1ull << winner;
-                // owner lane performs IoTSensor.collect_data (iot_sensors.py:127-145)
-                Real got = Real(0), urg_w = Real(0);
-                int in_range = 0;
-#pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    if (lane + 32 * k == winner) {
-                        const Real rc = s[k].det + dr.winner_draw(winner);
-                        in_range = rc >= p.thr;
-                        if (in_range && s[k].buf > Real(0)) {
-                            const Real cap = (Real)data_rate_of(s[k].sf) * p.cd;
-                            got = s[k].buf < cap ? s[k].buf : cap;
-                            s[k].buf -= got;
-                            s[k].tx += got;
-                        }
-                        urg_w = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], r.elapsed_s));
-                    }
-                }
-                const int owner = winner & 31;
-                got = shfl(got, owner);
-                urg_w = shfl(urg_w, owner);
-                in_range = shfl(in_range, owner);
-                urg_list[nwin < 6 ? nwin : 5] = urg_w;
-                nwin += 1;
-                if (in_range && got > Real(0)) {
-                    total_bytes += got;
-                    r.total_data_collected += (double)got;
-                    r.delivered += 1;
-                    const bool seen = winner < 32 ? (r.visited_lo >> winner) & 1u : (r.visited_hi >> (winner - 32)) & 1u;
-                    if (!seen) {
-                        any_new = true;
-                        if (winner < 32)
-                            r.visited_lo |= 1u << winner;
-                        else
-                            r.visited_hi |= 1u << (winner - 32);
-                    }
-                }
-            }
-        }
-        // Phase 5: fairness metrics (uav_env.py:596-604)
-        unsigned empty_b = 0u, nonempty_b = 0u;
-        float diff[SPL];
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            empty_b |= __ballot_sync(kFull, s[k].active && s[k].buf <= Real(0));
-            nonempty_b |= __ballot_sync(kFull, s[k].active && !(s[k].buf <= Real(0)));
-            const float after = s[k].active ? (float)(s[k].buf / p.rate) : 0.f;
-            const float d = before[k] - after;
-            diff[k] = d > 0.f ? d : 0.f;
-        }
-        was_empty = empty_b != 0u;
-        all_collected = nonempty_b == 0u;
-        urg_red = (Real)sensor_sum<Real, SPL>(diff, N, lane, sc.red, kSumNumpy);  // float32 np.sum
-        r.last_step_bytes = (float)total_bytes;
-        if (nwin > 0) {  // np.mean over the winners, in SF first-appearance order (uav_env.py:610-615)
-            Real acc = Real(0);
-            for (int w = 0; w < nwin && w < 6; ++w) acc += urg_list[w];
-            mean_urg = acc / (Real)nwin;
-        }
-        // Phase 6: reward_function.py:81-128, same order of additions
-        reward = p.p_step + p.p_hover;
-        if (total_bytes > Real(0)) {
-            reward += p.r_per_byte * total_bytes * mean_urg;
-            if (any_new) reward += p.r_new;
-        }
-        if (urg_red > Real(0)) reward += p.r_urg_red * urg_red;
-        if (was_empty && total_bytes == Real(0)) reward += p.p_revisit;
-        reward += p.p_battery * used;
-        if (collisions > 0) reward += p.p_collision * (Real)collisions;
-        if (step_loss > Real(0)) reward += p.p_data_loss * step_loss;
-        if (N > 1) {  // calculate_starvation_penalty, reward_function.py:46-57
-            Real mx = Real(0);
-#pragma unroll
-            for (int k = 0; k < SPL; ++k)
-                if (s[k].active) mx = s[k].buf > mx ? s[k].buf : mx;
-            mx = warp_max(mx);
-            if (mx != Real(0)) {
-                Real nrm[SPL], dev[SPL];
+        for (int k = 0; k < SPL; ++k)
+            if (s[k].active) mx = s[k].buf > mx ? s[k].buf : mx;
+        mx = warp_max(mx);
+        if (mx != Real(0)) {
+            Real nrm[SPL], dev[SPL];
+            if constexpr (kParity) {
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf / mx : Real(0);
-                const Real mean = sensor_sum<Real, SPL>(nrm, N, lane, sc.red, kSumNumpy) / (Real)N;
+            } else {
+                const float inv = __frcp_rn(mx);
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    const Real d = nrm[k] - mean;
-                    dev[k] = s[k].active ? d * d : Real(0);
-                }
-                reward += p.p_starvation * (sensor_sum<Real, SPL>(dev, N, lane, sc.red, kSumNumpy) / (Real)N);
+                for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf * inv : 0.f;
+            }
+            const Real mean = fdiv(sensor_sum<Real, SPL>(nrm, N, lane, ws.red, kSumNumpy), (Real)N);
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const Real d = nrm[k] - mean;
+                dev[k] = s[k].active ? d * d : Real(0);
+            }
+            reward += p.p_starvation * fdiv(sensor_sum<Real, SPL>(dev, N, lane, ws.red, kSumNumpy), (Real)N);
+        }
+    }
+    if (all_collected) reward += p.r_completion;
+    out.reward = reward;
+    out.total_bytes = total_bytes;
+    out.urg_red = urg_red;
+    out.mean_urg = mean_urg;
+    out.collisions = collisions;
+    out.captures = captures;
+    out.delivered = delivered;
+    out.any_new = any_new;
+    out.was_empty = was_empty;
+    out.all_collected = all_collected;
+    out.att_mask = att_mask;
+    out.win_mask = win_mask;
+}
+
+// One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
+// full residency and each warp walks environments e = warp_id, warp_id + total_warps, ...
+template <typename Real, bool REPLAY, int SPL>
+__global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
+    step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
+                const int32_t* __restrict__ actions) {
+    __shared__ WarpSmem smem[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& ws = smem[warp];
+    uavsim_env_record& R = ws.rec;
+    constexpr bool kParity = std::is_same<Real, double>::value;
+
+    for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
+        const int action = actions[e];
+        if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
+            if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+            continue;
+        }
+        load_record(ws, b.rec + e, lane);
+        Hot h = read_hot(R);
+        const int N = h.N;
+        Sensor<Real> s[SPL];
+        load_sensors<Real, SPL>(b, p, e, N, lane, s);
+
+        // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
+        h.step += 1;
+        int edge_delta = 0;
+        {
+            const double W = h.W, H = h.H, ux = h.x, uy = h.y, eps = 1e-6;
+            if (ux <= eps || uy <= eps || ux >= W - 1 - eps || uy >= H - 1 - eps) edge_delta = 1;
+        }
+        const bool collect = action == 4;
+        const Real dt = collect ? p.cd : Real(1);
+        h.elapsed += (float)dt;
+
+        const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+        Draws<Real, REPLAY, SPL> dr;
+        dr.P = p.P;
+        dr.sigma = p.sigma;
+        dr.k0 = p.key0;
+        dr.k1 = p.key1;
+        dr.env_lo = (uint32_t)gid;
+        dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
+        dr.episode = h.episode - 1;  // R.episode counts resets done; the running episode is one less
+        dr.step = (uint32_t)h.step;
+        dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+        dr.exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+        if (!REPLAY && dr.exp) {
+            const Real nan = Real(CUDART_NAN);
+            for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) dr.exp[i] = nan;
+            __syncwarp();
+        }
+        StepDraws<Real, SPL> sd;
+        dr.generate(lane, collect, sd);
+
+        // ---- iot_sensors.py:114-125: age the buffers ----
+        Real loss[SPL];
+        const Real nw = p.rate * dt;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            if constexpr (kParity) s[k].gen += nw;
+            const Real pot = s[k].buf + nw;
+            const bool over = pot > p.maxbuf;
+            loss[k] = over ? pot - p.maxbuf : Real(0);
+            s[k].buf = over ? p.maxbuf : pot;
+            s[k].lost += loss[k];  // + 0 when not saturated: no effect on the stored value
+        }
+        const Real step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
+
+        Real reward;
+        CollectOut<Real> co;
+        co.total_bytes = co.urg_red = co.mean_urg = Real(0);
+        co.collisions = co.captures = co.delivered = 0;
+        co.any_new = co.was_empty = co.all_collected = false;
+        co.att_mask = co.win_mask = 0ull;
+        int boundary_delta = 0;
+        if (!collect) {
+            // ---- uav.py:127-185 + reward_function.py:69-79 + uav_env.py:494-516 ----
+            float nx = h.x, ny = h.y;
+            if (action == 0)
+                ny += 1.0f;
+            else if (action == 1)
+                ny -= 1.0f;
+            else if (action == 2)
+                nx -= 1.0f;
+            else
+                nx += 1.0f;
+            const double before = h.battery;
+            const bool ok = (0.f <= nx) && (nx < (float)h.W) && (0.f <= ny) && (ny < (float)h.H);
+            if (ok) {
+                h.x = nx;
+                h.y = ny;
+                h.battery -= p.e_move;
+            } else {
+                h.battery -= p.e_fail;
+                boundary_delta = 1;
+            }
+            const Real used = (Real)(before - h.battery);
+            reward = p.p_step;
+            reward += ok ? p.r_move : p.p_boundary;
+            reward += p.p_battery * used;
+            reward += p.p_data_loss * step_loss;
+            compute_det(p, h.x, h.y, s);  // for the observation at the new position
+        } else {
+            compute_det(p, h.x, h.y, s);
+            collect_action<Real, REPLAY, SPL>(p, h, s, sd, dr, step_loss, lane, ws, co);
+            reward = co.reward;
+        }
+
+        // ---- uav_env.py:471-485: truncation + terminal penalties ----
+        bool truncated = false;
+        if (!(h.battery > p.batt_floor)) truncated = true;  // uav.py:224
+        if (h.step >= p.max_steps) truncated = true;
+        if (truncated) {
+            const int unvisited = N - (__popc(h.vis_lo) + __popc(h.vis_hi));
+            if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
+            int starved = 0;  // reward_function.py:59-67
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const Real g = generated_of(p, s[k], h.elapsed);
+                starved += __popc(__ballot_sync(kFull, s[k].active && g > Real(0) && fdiv(s[k].tx, g) < p.cr_thr));
+            }
+            Real pen = Real(0);
+            for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
+            reward += pen;
+        }
+
+        // ---- observation (uav_env.py:638-674) ----
+        float* obs_row = b.obs + (size_t)e * p.obs_stride;
+        observe<Real, SPL>(p, h, s, sd, lane, ws.obs, obs_row);
+
+        // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
+        Real shaped = reward;
+        bool full_cov = false;
+        if (p.domain_rand) {
+            const float cur = nearest_with_data(h.x, h.y, s);
+            if (h.prev_dist > 0.f) {
+                if constexpr (kParity)
+                    shaped += p.prox_eta * ((double)h.prev_dist - (double)cur);
+                else
+                    shaped += p.prox_eta * (h.prev_dist - cur);
+            }
+            h.prev_dist = cur;
+            full_cov = (__popc(h.vis_lo) + __popc(h.vis_hi)) == N;
+            Real r1[SPL], r2[SPL];
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const Real g = generated_of(p, s[k], h.elapsed);
+                const bool has = s[k].active && g > Real(0);
+                const Real rate = has ? fdiv(s[k].tx, g) * Real(100) : Real(0);
+                r1[k] = rate;
+                r2[k] = rate * rate;
+                cnt += __popc(__ballot_sync(kFull, has));
+            }
+            if (cnt > 0) {
+                const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
+                const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
+                const Real jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
+                shaped += fdiv(p.jain_bonus * (jain - Real(0.5)), (Real)N);
             }
         }
-        if (all_collected) reward += p.r_completion;
-        r.collisions += collisions;
+
+        // ---- commit the record (lane 0) and write the per-env outputs ----
+        const bool restart = truncated && p.auto_reset;
+        if (lane == 0) {
+            R.x = h.x;
+            R.y = h.y;
+            R.battery = h.battery;
+            R.elapsed_s = h.elapsed;
+            R.prev_dist_nearest = h.prev_dist;
+            R.step = h.step;
+            R.visited_lo = h.vis_lo;
+            R.visited_hi = h.vis_hi;
+            R.total_reward += (double)reward;            // uav_env.py:487
+            R.episode_return += (double)shaped;
+            R.total_data_collected += (double)co.total_bytes;
+            R.last_step_bytes = (float)co.total_bytes;
+            R.capture_triggers += co.captures;
+            R.boundary_hits += boundary_delta;
+            R.edge_steps += edge_delta;
+            R.collisions += co.collisions;
+            R.delivered += co.delivered;
+            if (p.domain_rand && full_cov && R.first_full_coverage_step < 0) R.first_full_coverage_step = h.step;
+            reinterpret_cast<Real*>(b.reward)[e] = shaped;
+            b.done[e] = truncated ? 1 : 0;
+            if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(h.x, h.y, h.W, h.H);
+            if (b.step_detail) {
+                double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+                d[UAVSIM_DETAIL_COLLISIONS] = co.collisions;
+                d[UAVSIM_DETAIL_BYTES] = (double)co.total_bytes;
+                d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)co.urg_red;
+                d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)co.mean_urg;
+                d[UAVSIM_DETAIL_WAS_NEW] = co.any_new;
+                d[UAVSIM_DETAIL_WAS_EMPTY] = co.was_empty;
+                d[UAVSIM_DETAIL_ALL_COLLECTED] = co.all_collected;
+                d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
+                d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)co.att_mask;
+                d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(co.att_mask >> 32);
+                d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)co.win_mask;
+                d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(co.win_mask >> 32);
+                d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
+                d[UAVSIM_DETAIL_TRUNCATED] = truncated;
+                d[14] = 0.0;
+                d[15] = 0.0;
+            }
+        }
+
+        // ---- SB3 VecEnv semantics: finished episodes restart inside the same call ----
+        if (restart) {
+            __syncwarp();
+            if (b.terminal_obs) {
+                const int n = 3 + p.fps * N;
+                float* t = b.terminal_obs + (size_t)e * p.obs_dim;
+                for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? ws.obs[i] : 0.0f;
+            }
+            write_episode_stats<Real, SPL>(p, b, e, lane, R, s);
+            reset_env<Real, REPLAY, SPL>(p, b, e, lane, ws, s, (Real*)nullptr);
+        }
+        store_sensors<Real, SPL>(b, p, e, lane, s, restart);
+        store_record(ws, b.rec + e, lane);
     }
-
-    // ---- uav_env.py:471-485: truncation + terminal penalties ----
-    bool truncated = false;
-    if (!(r.battery > p.batt_floor)) truncated = true;  // uav.py:224
-    if (r.step >= p.max_steps) truncated = true;
-    if (truncated) {
-        const int unvisited = N - (__popc(r.visited_lo) + __popc(r.visited_hi));
-        if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
-        int starved = 0;  // reward_function.py:59-67
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            const Real g = generated_of(p, s[k], r.elapsed_s);
-            starved += __popc(__ballot_sync(kFull, s[k].active && g > Real(0) && (s[k].tx / g) < p.cr_thr));
-        }
-        Real pen = Real(0);
-        for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
-        reward += pen;
-    }
-    r.total_reward += (double)reward;
-
-    // ---- observation (uav_env.py:638-674) ----
-    float* obs_row = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, REPLAY, SPL>(p, r, s, dr, lane, sc.obs, obs_row);
-
-    // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
-    Real shaped = reward;
-    if (p.domain_rand) {
-        const float cur = nearest_with_data(r, s);
-        if (prev_dist > 0.f) {
-            if constexpr (kParity)
-                shaped += p.prox_eta * ((double)prev_dist - (double)cur);
-            else
-                shaped += p.prox_eta * (prev_dist - cur);
-        }
-        r.prev_dist_nearest = cur;
-        if (r.first_full_coverage_step < 0 && (__popc(r.visited_lo) + __popc(r.visited_hi)) == N)
-            r.first_full_coverage_step = r.step;
-        Real r1[SPL], r2[SPL];
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            const Real g = generated_of(p, s[k], r.elapsed_s);
-            const bool has = s[k].active && g > Real(0);
-            const Real rate = has ? (s[k].tx / g) * Real(100) : Real(0);
-            r1[k] = rate;
-            r2[k] = rate * rate;
-            cnt += __popc(__ballot_sync(kFull, has));
-        }
-        if (cnt > 0) {
-            const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, sc.red, kSumSequential);
-            const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, sc.red, kSumSequential);
-            const Real jain = s2 > Real(0) ? (s1 * s1) / ((Real)cnt * s2) : Real(1);
-            shaped += p.jain_bonus * (jain - Real(0.5)) / (Real)N;
-        }
-    }
-    r.episode_return += (double)shaped;
-
-    // ---- outputs ----
-    if (lane == 0) {
-        reinterpret_cast<Real*>(b.reward)[e] = shaped;
-        b.done[e] = truncated ? 1 : 0;
-        if (b.step_detail) {
-            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
-            d[UAVSIM_DETAIL_COLLISIONS] = collisions;
-            d[UAVSIM_DETAIL_BYTES] = (double)total_bytes;
-            d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)urg_red;
-            d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)mean_urg;
-            d[UAVSIM_DETAIL_WAS_NEW] = any_new;
-            d[UAVSIM_DETAIL_WAS_EMPTY] = was_empty;
-            d[UAVSIM_DETAIL_ALL_COLLECTED] = all_collected;
-            d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
-            d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)att_mask;
-            d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(att_mask >> 32);
-            d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)win_mask;
-            d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(win_mask >> 32);
-            d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
-            d[UAVSIM_DETAIL_TRUNCATED] = truncated;
-            d[14] = 0.0;
-            d[15] = 0.0;
-        }
-    }
-
-    // ---- SB3 VecEnv semantics: finished episodes restart inside the same call ----
-    bool layout_changed = false;
-    if (truncated && p.auto_reset) {
-        if (b.terminal_obs) {
-            const int n = 3 + p.fps * N;
-            float* t = b.terminal_obs + (size_t)e * p.obs_dim;
-            for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? sc.obs[i] : 0.0f;
-        }
-        write_episode_stats<Real, SPL>(p, b, e, lane, r, s);
-        reset_env<Real, REPLAY, SPL>(p, b, e, lane, r, s, sc, layout_changed, (Real*)nullptr);
-        r.episode += 1;
-    } else if (b.action_mask && lane == 0) {
-        b.action_mask[e] = action_mask_of(r.x, r.y, r.grid_w, r.grid_h);
-    }
-
-    store_sensors<Real, SPL>(b, p, e, lane, s, (truncated && p.auto_reset));
-    if (lane == 0) b.rec[e] = r;
 }
 
 }  // namespace uavsim

@@ -13,41 +13,67 @@ cudaError_t launch_step_f32(const Params<float>& p, const Buffers& b, const int3
 cudaError_t launch_reset_f32(const Params<float>& p, const Buffers& b, const uint8_t* mask, bool replay,
                              cudaStream_t st);
 
+// Persistent grid: one wave of blocks at full residency (SM count x occupancy), never more blocks than
+// there are groups of kWarpsPerBlock environments.
+template <typename Kernel>
+inline int persistent_grid(Kernel k, int E) {
+    static int blocks_per_wave = 0;  // one static per kernel instantiation
+    if (blocks_per_wave == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, 0);
+        blocks_per_wave = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
+    }
+    const int need = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return need < blocks_per_wave ? need : blocks_per_wave;
+}
+
 template <typename Real>
 inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const int32_t* actions, bool replay,
                                  cudaStream_t st) {
-    const int grid = (b.E + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool two = p.P > 32;
+#define UAVSIM_LAUNCH_STEP(R, S)                                                              \
+    do {                                                                                      \
+        auto k = step_kernel<Real, R, S>;                                                     \
+        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                       \
+    } while (0)
     if (replay) {
         if (two)
-            step_kernel<Real, true, 2><<<grid, kThreads, 0, st>>>(p, b, actions);
+            UAVSIM_LAUNCH_STEP(true, 2);
         else
-            step_kernel<Real, true, 1><<<grid, kThreads, 0, st>>>(p, b, actions);
+            UAVSIM_LAUNCH_STEP(true, 1);
     } else {
         if (two)
-            step_kernel<Real, false, 2><<<grid, kThreads, 0, st>>>(p, b, actions);
+            UAVSIM_LAUNCH_STEP(false, 2);
         else
-            step_kernel<Real, false, 1><<<grid, kThreads, 0, st>>>(p, b, actions);
+            UAVSIM_LAUNCH_STEP(false, 1);
     }
+#undef UAVSIM_LAUNCH_STEP
     return cudaGetLastError();
 }
 
 template <typename Real>
 inline cudaError_t launch_reset_t(const Params<Real>& p, const Buffers& b, const uint8_t* mask, bool replay,
                                   cudaStream_t st) {
-    const int grid = (b.E + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool two = p.P > 32;
+#define UAVSIM_LAUNCH_RESET(R, S)                                                             \
+    do {                                                                                      \
+        auto k = reset_kernel<Real, R, S>;                                                    \
+        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, mask);                          \
+    } while (0)
     if (replay) {
         if (two)
-            reset_kernel<Real, true, 2><<<grid, kThreads, 0, st>>>(p, b, mask);
+            UAVSIM_LAUNCH_RESET(true, 2);
         else
-            reset_kernel<Real, true, 1><<<grid, kThreads, 0, st>>>(p, b, mask);
+            UAVSIM_LAUNCH_RESET(true, 1);
     } else {
         if (two)
-            reset_kernel<Real, false, 2><<<grid, kThreads, 0, st>>>(p, b, mask);
+            UAVSIM_LAUNCH_RESET(false, 2);
         else
-            reset_kernel<Real, false, 1><<<grid, kThreads, 0, st>>>(p, b, mask);
+            UAVSIM_LAUNCH_RESET(false, 1);
     }
+#undef UAVSIM_LAUNCH_RESET
     return cudaGetLastError();
 }
 

@@ -156,6 +156,8 @@ Params<Real> make_params(const uavsim_config& c) {
     p.e_hover = (c.power_hover_w * c.collection_duration) / 3600;          // uav.py:205
     p.used_hover = (c.power_hover_w / (60 * 60)) * c.collection_duration;  // uav.py:263, uav_env.py:530
     p.inv_max_battery = (float)(1.0 / c.max_battery);
+    p.inv_maxbuf = (float)(1.0 / c.max_buffer_size);
+    p.inv_rate = (float)(1.0 / c.data_generation_rate);
     p.min_start_dist = c.min_start_dist;
     p.max_steps = c.max_steps;
     p.init_sf = c.init_sf;

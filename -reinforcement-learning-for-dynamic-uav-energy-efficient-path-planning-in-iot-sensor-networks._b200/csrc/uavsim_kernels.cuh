@@ -69,7 +69,7 @@ struct Params {
     Real prox_eta, jain_bonus;
     // UAV energy (always float64: a handful of per-env scalars)
     double max_battery, batt_floor, e_move, e_fail, e_hover, used_hover;
-    float inv_max_battery;
+    float inv_max_battery, inv_maxbuf, inv_rate;
     double min_start_dist;
     int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
     int32_t grids[UAVSIM_MAX_GRIDS][2];
@@ -174,6 +174,26 @@ __device__ __forceinline__ Real fdiv(Real a, Real b) {
         return a / b;
     else
         return __fdividef(a, b);
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// x / c for a per-handle constant c: IEEE division in the parity build, multiply by the precomputed
+// reciprocal in the throughput build
+template <typename Real>
+__device__ __forceinline__ Real div_const(Real x, Real c, float inv_c) {
+    if constexpr (std::is_same<Real, double>::value)
+        return x / c;
+    else
+        return x * inv_c;
 }
 
 enum SumOrder { kSumNumpy, kSumSequential };
@@ -296,7 +316,7 @@ __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Rea
 // UAVEnvironment._calculate_urgency (uav_env.py:376-384)
 template <typename Real>
 __device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real lost, Real gen) {
-    const Real util = fdiv(buf, p.maxbuf);
+    const Real util = div_const(buf, p.maxbuf, p.inv_maxbuf);
     const Real lr = gen > Real(0) ? fdiv(lost, gen) : Real(0);
     const Real u = util * (Real(1) + lr * Real(10));
     return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
@@ -318,7 +338,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, Real sigma, R
     } else {
         const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
         const float u2 = (float)b * 2.3283064365386963e-10f;
-        const float r = sigma * sqrtf(-1.3862943611198906f * __log2f(u1));  // -2 ln u = -2 ln2 lg2 u
+        const float r = sigma * fast_sqrt(-1.3862943611198906f * __log2f(u1));  // -2 ln u = -2 ln2 lg2 u
         float s, c;
         __sincosf(6.2831853071795865f * u2, &s, &c);
         z0 = r * c;
@@ -562,23 +582,24 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 // Mutates EMA / SF (draw D) and range-checks (draw E).  The row is staged in shared memory and written
 // with consecutive lanes on consecutive floats; ghost slots are zero-filled when the buffer is bound /
 // an episode starts and never touched by a step (N is fixed during an episode).
-template <typename Real, int SPL>
+template <typename Real, int SPL, int FPS>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
                                         const StepDraws<Real, SPL>& sd, int lane, float* stage, float* out) {
+    constexpr bool kParity = std::is_same<Real, double>::value;
     __syncwarp();
     float inv_w = 0.f, inv_h = 0.f;
-    if constexpr (!std::is_same<Real, double>::value) {
-        inv_w = __frcp_rn((float)h.W);
-        inv_h = __frcp_rn((float)h.H);
+    if constexpr (!kParity && FPS == 5) {
+        inv_w = fast_rcp((float)h.W);
+        inv_h = fast_rcp((float)h.H);
     }
     if (lane == 0) {
-        if constexpr (std::is_same<Real, double>::value) {
+        if constexpr (kParity) {
             stage[0] = (float)((double)h.x / (double)h.W);
             stage[1] = (float)((double)h.y / (double)h.H);
             stage[2] = (float)(h.battery / p.max_battery);
         } else {
-            stage[0] = h.x * inv_w;
-            stage[1] = h.y * inv_h;
+            stage[0] = __fdividef(h.x, (float)h.W);
+            stage[1] = __fdividef(h.y, (float)h.H);
             stage[2] = (float)h.battery * p.inv_max_battery;
         }
     }
@@ -589,12 +610,12 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
         adr_update(p, s[k].det + sd.d[k], s[k].ema, s[k].sf);
         const bool in_range = (s[k].det + sd.e[k]) >= p.thr;
         if (s[k].active) {
-            float* o = stage + 3 + p.fps * j;
-            o[0] = (float)fdiv(s[k].buf, p.maxbuf);
+            float* o = stage + 3 + FPS * j;
+            o[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
             o[1] = (float)urg;
             o[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
-            if (p.fps == 5) {  // include_sensor_positions, uav_env.py:668-672
-                if constexpr (std::is_same<Real, double>::value) {
+            if constexpr (FPS == 5) {  // include_sensor_positions, uav_env.py:668-672
+                if constexpr (kParity) {
                     o[3] = (float)(((double)s[k].sx - (double)h.x) / (double)h.W);
                     o[4] = (float)(((double)s[k].sy - (double)h.y) / (double)h.H);
                 } else {
@@ -605,8 +626,13 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
         }
     }
     __syncwarp();
-    const int n = 3 + p.fps * h.N;
-    for (int i = lane; i < n; i += 32) out[i] = stage[i];
+    const int n = 3 + FPS * h.N;
+    constexpr int kIters = (3 + FPS * 32 * SPL + 31) / 32;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const int i = lane + 32 * it;
+        if (i < n) out[i] = stage[i];
+    }
 }
 
 // DomainRandEnv._dist_to_nearest_with_data (dqn.py:405-412): float32 norm, min over sensors with data.
@@ -701,8 +727,8 @@ __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const
 // registers; writes the first observation.  FIXED: UAVEnvironment.reset (uav_env.py:400-427,
 // iot_sensors.py:305-321).  DOMAIN_RAND: DomainRandEnv.reset (dqn.py:301-372).  ws.rec.episode names
 // the NEW episode on entry and is incremented on exit.
-template <typename Real, bool REPLAY, int SPL>
-__device__ __noinline__ void reset_env(const Params<Real>& p, const Buffers& b, int e, int lane, WarpSmem& ws,
+template <typename Real, bool REPLAY, int SPL, int FPS>
+__device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& b, int e, int lane, WarpSmem& ws,
                                        Sensor<Real> (&s)[SPL], Real* exp) {
     uavsim_env_record& R = ws.rec;
     __syncwarp();
@@ -874,8 +900,8 @@ __device__ __noinline__ void reset_env(const Params<Real>& p, const Buffers& b, 
     StepDraws<Real, SPL> sd;
     dr.generate(lane, false, sd);
     float* out = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, SPL>(p, h, s, sd, lane, ws.obs, out);
-    for (int i = 3 + p.fps * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
+    observe<Real, SPL, FPS>(p, h, s, sd, lane, ws.obs, out);
+    for (int i = 3 + FPS * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
     const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
     __syncwarp();
     if (lane == 0) {
@@ -909,7 +935,7 @@ constexpr int min_blocks_per_sm() {
     return std::is_same<Real, double>::value ? 1 : 3;
 }
 
-template <typename Real, bool REPLAY, int SPL>
+template <typename Real, bool REPLAY, int SPL, int FPS>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     reset_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b, const uint8_t* mask) {
     __shared__ WarpSmem smem[kWarpsPerBlock];
@@ -926,7 +952,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
             for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
             __syncwarp();
         }
-        reset_env<Real, REPLAY, SPL>(p, b, e, lane, ws, s, exp);
+        reset_env<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws, s, exp);
         store_sensors<Real, SPL>(b, p, e, lane, s, true);
         store_record(ws, b.rec + e, lane);
         if (lane == 0 && b.done) b.done[e] = 0;
@@ -971,7 +997,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
     const int N = h.N;
     float before[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; ++k) before[k] = (float)fdiv(s[k].buf, p.rate);  // _get_sensor_urgencies, :386-394
+    for (int k = 0; k < SPL; ++k) before[k] = (float)div_const(s[k].buf, p.rate, p.inv_rate);  // _get_sensor_urgencies, :386-394
     h.battery -= p.e_hover;                                                    // uav.py:205
     const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
     // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
@@ -1103,7 +1129,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
     for (int k = 0; k < SPL; ++k) {
         empty_b |= __ballot_sync(kFull, s[k].active && s[k].buf <= Real(0));
         nonempty_b |= __ballot_sync(kFull, s[k].active && !(s[k].buf <= Real(0)));
-        const float d = before[k] - (float)fdiv(s[k].buf, p.rate);
+        const float d = before[k] - (float)div_const(s[k].buf, p.rate, p.inv_rate);
         diff[k] = d > 0.f ? d : 0.f;
     }
     const bool was_empty = empty_b != 0u, all_collected = nonempty_b == 0u;
@@ -1132,7 +1158,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf / mx : Real(0);
             } else {
-                const float inv = __frcp_rn(mx);
+                const float inv = fast_rcp(mx);
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf * inv : 0.f;
             }
@@ -1162,7 +1188,26 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks environments e = warp_id, warp_id + total_warps, ...
-template <typename Real, bool REPLAY, int SPL>
+// Episode end inside a step (SB3 VecEnv semantics): terminal observation, episode statistics, new episode.
+// Deliberately NOT inlined and self-contained -- it re-reads the sensor columns the step has just stored
+// -- so that the rare path costs the hot loop neither registers nor local memory.
+template <typename Real, bool REPLAY, int SPL, int FPS>
+__device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buffers& b, int e, int lane, WarpSmem& ws) {
+    __syncwarp();
+    const int N = ws.rec.num_sensors;
+    if (b.terminal_obs) {
+        const int n = 3 + FPS * N;
+        float* t = b.terminal_obs + (size_t)e * p.obs_dim;
+        for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? ws.obs[i] : 0.0f;
+    }
+    Sensor<Real> s[SPL];
+    load_sensors<Real, SPL>(b, p, e, N, lane, s);
+    write_episode_stats<Real, SPL>(p, b, e, lane, ws.rec, s);
+    reset_env<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws, s, (Real*)nullptr);
+    store_sensors<Real, SPL>(b, p, e, lane, s, true);
+}
+
+template <typename Real, bool REPLAY, int SPL, int FPS>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
@@ -1187,9 +1232,12 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
         h.step += 1;
         int edge_delta = 0;
-        {
+        if constexpr (kParity) {
             const double W = h.W, H = h.H, ux = h.x, uy = h.y, eps = 1e-6;
             if (ux <= eps || uy <= eps || ux >= W - 1 - eps || uy >= H - 1 - eps) edge_delta = 1;
+        } else {
+            const float eps = 1e-6f;
+            if (h.x <= eps || h.y <= eps || h.x >= (float)(h.W - 1) - eps || h.y >= (float)(h.H - 1) - eps) edge_delta = 1;
         }
         const bool collect = action == 4;
         const Real dt = collect ? p.cd : Real(1);
@@ -1227,7 +1275,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
             s[k].buf = over ? p.maxbuf : pot;
             s[k].lost += loss[k];  // + 0 when not saturated: no effect on the stored value
         }
-        const Real step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
+        bool any_over = false;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) any_over |= (s[k].active && loss[k] > Real(0));
+        Real step_loss = Real(0);
+        if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
 
         Real reward;
         CollectOut<Real> co;
@@ -1289,7 +1341,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
 
         // ---- observation (uav_env.py:638-674) ----
         float* obs_row = b.obs + (size_t)e * p.obs_stride;
-        observe<Real, SPL>(p, h, s, sd, lane, ws.obs, obs_row);
+        observe<Real, SPL, FPS>(p, h, s, sd, lane, ws.obs, obs_row);
 
         // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
         Real shaped = reward;
@@ -1326,24 +1378,30 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         // ---- commit the record (lane 0) and write the per-env outputs ----
         const bool restart = truncated && p.auto_reset;
         if (lane == 0) {
-            R.x = h.x;
-            R.y = h.y;
+            if (!collect) {
+                R.x = h.x;
+                R.y = h.y;
+                if (boundary_delta) R.boundary_hits += 1;
+                if (R.last_step_bytes != 0.f) R.last_step_bytes = 0.f;
+            } else {
+                R.visited_lo = h.vis_lo;
+                R.visited_hi = h.vis_hi;
+                R.total_data_collected += (double)co.total_bytes;
+                R.last_step_bytes = (float)co.total_bytes;
+                R.capture_triggers += co.captures;
+                R.collisions += co.collisions;
+                R.delivered += co.delivered;
+            }
             R.battery = h.battery;
             R.elapsed_s = h.elapsed;
-            R.prev_dist_nearest = h.prev_dist;
             R.step = h.step;
-            R.visited_lo = h.vis_lo;
-            R.visited_hi = h.vis_hi;
             R.total_reward += (double)reward;            // uav_env.py:487
             R.episode_return += (double)shaped;
-            R.total_data_collected += (double)co.total_bytes;
-            R.last_step_bytes = (float)co.total_bytes;
-            R.capture_triggers += co.captures;
-            R.boundary_hits += boundary_delta;
-            R.edge_steps += edge_delta;
-            R.collisions += co.collisions;
-            R.delivered += co.delivered;
-            if (p.domain_rand && full_cov && R.first_full_coverage_step < 0) R.first_full_coverage_step = h.step;
+            if (edge_delta) R.edge_steps += 1;
+            if (p.domain_rand) {
+                R.prev_dist_nearest = h.prev_dist;
+                if (full_cov && R.first_full_coverage_step < 0) R.first_full_coverage_step = h.step;
+            }
             reinterpret_cast<Real*>(b.reward)[e] = shaped;
             b.done[e] = truncated ? 1 : 0;
             if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(h.x, h.y, h.W, h.H);
@@ -1369,17 +1427,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         }
 
         // ---- SB3 VecEnv semantics: finished episodes restart inside the same call ----
-        if (restart) {
-            __syncwarp();
-            if (b.terminal_obs) {
-                const int n = 3 + p.fps * N;
-                float* t = b.terminal_obs + (size_t)e * p.obs_dim;
-                for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? ws.obs[i] : 0.0f;
-            }
-            write_episode_stats<Real, SPL>(p, b, e, lane, R, s);
-            reset_env<Real, REPLAY, SPL>(p, b, e, lane, ws, s, (Real*)nullptr);
-        }
-        store_sensors<Real, SPL>(b, p, e, lane, s, restart);
+        store_sensors<Real, SPL>(b, p, e, lane, s, false);
+        if (restart) finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
         store_record(ws, b.rec + e, lane);
     }
 }

@@ -35,8 +35,13 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
     const bool two = p.P > 32;
 #define UAVSIM_LAUNCH_STEP(R, S)                                                              \
     do {                                                                                      \
-        auto k = step_kernel<Real, R, S>;                                                     \
-        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                       \
+        if (p.fps == 5) {                                                                     \
+            auto k = step_kernel<Real, R, S, 5>;                                              \
+            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                   \
+        } else {                                                                              \
+            auto k = step_kernel<Real, R, S, 3>;                                              \
+            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                   \
+        }                                                                                     \
     } while (0)
     if (replay) {
         if (two)
@@ -59,8 +64,13 @@ inline cudaError_t launch_reset_t(const Params<Real>& p, const Buffers& b, const
     const bool two = p.P > 32;
 #define UAVSIM_LAUNCH_RESET(R, S)                                                             \
     do {                                                                                      \
-        auto k = reset_kernel<Real, R, S>;                                                    \
-        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, mask);                          \
+        if (p.fps == 5) {                                                                     \
+            auto k = reset_kernel<Real, R, S, 5>;                                             \
+            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, mask);                      \
+        } else {                                                                              \
+            auto k = reset_kernel<Real, R, S, 3>;                                             \
+            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, mask);                      \
+        }                                                                                     \
     } while (0)
     if (replay) {
         if (two)

@@ -66,6 +66,8 @@ int validate(const uavsim_config* c) {
     if (c->reset_mode != UAVSIM_RESET_FIXED && c->reset_mode != UAVSIM_RESET_DOMAIN_RAND)
         return fail(UAVSIM_ERR_INVALID_ARG, "reset_mode must be UAVSIM_RESET_FIXED or UAVSIM_RESET_DOMAIN_RAND");
     if (c->grid_w <= 0 || c->grid_h <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "grid must be positive");
+    if ((int64_t)c->num_envs * c->max_sensors >= (1ll << 32))
+        return fail(UAVSIM_ERR_INVALID_ARG, "num_envs * max_sensors must be < 2^32 per handle");
     if (c->max_steps <= 0 || c->max_steps >= (1 << 24))
         return fail(UAVSIM_ERR_INVALID_ARG, "max_steps must be in [1, 2^24)");
     if (!(c->data_generation_rate > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "data_generation_rate must be > 0");
@@ -449,6 +451,10 @@ int uavsim_get_field(uavsim_handle* h, int field, uavsim_field_view* v) {
             v->stride_bytes[1] = rb;
             break;
         case UAVSIM_FIELD_SENSOR_SF:
+            if (h->cfg.precision == UAVSIM_F32)
+                return fail(UAVSIM_ERR_UNSUPPORTED,
+                            "throughput layout: the spreading factor is packed into the low 3 mantissa bits of avg_rssi "
+                            "(sf = (bits & 7) + 7)");
             v->ptr = h->buf.ssf;
             v->elem_bytes = 1;
             v->is_float = 0;

@@ -451,7 +451,6 @@ struct Draws {
 struct alignas(16) WarpSmem {
     uavsim_env_record rec;           // this warp's environment record: one coalesced 128-byte load/store
     double red[UAVSIM_MAX_SENSORS];  // parity-build ordered reductions; far-start candidate search
-    float obs[kMaxObsDim + 1];       // observation row staging
 };
 
 // Scalars every lane needs in registers during a step (the rest of the record stays in shared memory).
@@ -505,12 +504,28 @@ __device__ __forceinline__ Real generated_of(const Params<Real>& p, const Sensor
         return fmaf(p.rate, elapsed, s.gen);  // total_data_generated = at_reset + rate * sum(dt)
 }
 
+// Throughput layout: the spreading factor rides in the three low mantissa bits of avg_rssi (code sf-7),
+// so a sensor's mutable state is ONE 16-byte vector.  avg_rssi is a decaying average of values with
+// 4 dB of noise; an 8-ulp (6e-5 dB) rounded quantisation per step is far below anything the model
+// resolves, and NaN (= None) keeps its payload bits.  The parity layout keeps the separate u8 column.
+__device__ __forceinline__ float pack_sf(float ema, int sf) {
+    const uint32_t b = (__float_as_uint(ema) + 4u) & ~7u;  // round to a multiple of 8 ulp
+    const uint32_t keep = (ema != ema) ? 0x7fc00000u : b;  // canonical NaN for None
+    return __uint_as_float(keep | (uint32_t)(sf - 7));
+}
+__device__ __forceinline__ void unpack_sf(float packed, float& ema, int& sf) {
+    const uint32_t b = __float_as_uint(packed);
+    sf = (int)(b & 7u) + 7;
+    ema = __uint_as_float(b & ~7u);
+}
+
 template <typename Real, int SPL>
 __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real>& p, int e, int N, int lane,
                                              Sensor<Real> (&s)[SPL]) {
-    const size_t row = (size_t)e * p.P;
-    const SensorState<Real>* st = reinterpret_cast<const SensorState<Real>*>(b.sstate) + row;
-    const Real* gen = reinterpret_cast<const Real*>(b.sgen) + row;
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    const uint32_t row = (uint32_t)e * (uint32_t)p.P;  // E*P < 2^32 (checked at create)
+    const SensorState<Real>* st = reinterpret_cast<const SensorState<Real>*>(b.sstate);
+    const Real* gen = reinterpret_cast<const Real*>(b.sgen);
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
@@ -527,10 +542,17 @@ __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real
         Real g = Real(0);
         int sf = 12;
         if (s[k].active) {
-            v = st[j];
-            xy = b.spos[row + j];
-            g = gen[j];
-            sf = b.ssf[row + j];
+            const uint32_t i = row + (uint32_t)j;
+            v = st[i];
+            xy = b.spos[i];
+            g = gen[i];
+            if constexpr (kParity) sf = b.ssf[i];
+        }
+        if constexpr (!kParity) {
+            float ema;
+            unpack_sf(v.ema, ema, sf);
+            if (!s[k].active) sf = 12;
+            v.ema = ema;
         }
         s[k].buf = v.buf;
         s[k].tx = v.tx;
@@ -546,23 +568,29 @@ __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real
 template <typename Real, int SPL>
 __device__ __forceinline__ void store_sensors(const Buffers& b, const Params<Real>& p, int e, int lane,
                                               const Sensor<Real> (&s)[SPL], bool write_static) {
-    const size_t row = (size_t)e * p.P;
-    SensorState<Real>* st = reinterpret_cast<SensorState<Real>*>(b.sstate) + row;
-    Real* gen = reinterpret_cast<Real*>(b.sgen) + row;
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    const uint32_t row = (uint32_t)e * (uint32_t)p.P;
+    SensorState<Real>* st = reinterpret_cast<SensorState<Real>*>(b.sstate);
+    Real* gen = reinterpret_cast<Real*>(b.sgen);
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
         if (s[k].active) {
+            const uint32_t i = row + (uint32_t)j;
             SensorState<Real> v;
             v.buf = s[k].buf;
             v.tx = s[k].tx;
             v.lost = s[k].lost;
-            v.ema = s[k].ema;
-            st[j] = v;
-            b.ssf[row + j] = (uint8_t)s[k].sf;
+            if constexpr (kParity) {
+                v.ema = s[k].ema;
+                b.ssf[i] = (uint8_t)s[k].sf;
+            } else {
+                v.ema = pack_sf(s[k].ema, s[k].sf);
+            }
+            st[i] = v;
             // parity build accumulates total_data_generated; throughput build only rewrites it on reset
-            if (std::is_same<Real, double>::value || write_static) gen[j] = s[k].gen;
-            if (write_static) b.spos[row + j] = make_float2(s[k].sx, s[k].sy);
+            if (kParity || write_static) gen[i] = s[k].gen;
+            if (write_static) b.spos[i] = make_float2(s[k].sx, s[k].sy);
         }
     }
 }
@@ -579,14 +607,14 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 }
 
 // UAVEnvironment._get_observation (uav_env.py:638-674) + zero padding to obs_slots (dqn.py:286-298).
-// Mutates EMA / SF (draw D) and range-checks (draw E).  The row is staged in shared memory and written
-// with consecutive lanes on consecutive floats; ghost slots are zero-filled when the buffer is bound /
-// an episode starts and never touched by a step (N is fixed during an episode).
+// Mutates EMA / SF (draw D) and range-checks (draw E).  Each lane stores its sensor's features straight
+// into the row (the partial sectors of neighbouring lanes merge in L2; DRAM sees the row once); ghost
+// slots are zero-filled when the buffer is bound / an episode starts and never touched by a step (N is
+// fixed during an episode).
 template <typename Real, int SPL, int FPS>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
-                                        const StepDraws<Real, SPL>& sd, int lane, float* stage, float* out) {
+                                        const StepDraws<Real, SPL>& sd, int lane, float* __restrict__ out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
-    __syncwarp();
     float inv_w = 0.f, inv_h = 0.f;
     if constexpr (!kParity && FPS == 5) {
         inv_w = fast_rcp((float)h.W);
@@ -594,13 +622,13 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
     }
     if (lane == 0) {
         if constexpr (kParity) {
-            stage[0] = (float)((double)h.x / (double)h.W);
-            stage[1] = (float)((double)h.y / (double)h.H);
-            stage[2] = (float)(h.battery / p.max_battery);
+            out[0] = (float)((double)h.x / (double)h.W);
+            out[1] = (float)((double)h.y / (double)h.H);
+            out[2] = (float)(h.battery / p.max_battery);
         } else {
-            stage[0] = __fdividef(h.x, (float)h.W);
-            stage[1] = __fdividef(h.y, (float)h.H);
-            stage[2] = (float)h.battery * p.inv_max_battery;
+            out[0] = __fdividef(h.x, (float)h.W);
+            out[1] = __fdividef(h.y, (float)h.H);
+            out[2] = (float)h.battery * p.inv_max_battery;
         }
     }
 #pragma unroll
@@ -610,7 +638,7 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
         adr_update(p, s[k].det + sd.d[k], s[k].ema, s[k].sf);
         const bool in_range = (s[k].det + sd.e[k]) >= p.thr;
         if (s[k].active) {
-            float* o = stage + 3 + FPS * j;
+            float* o = out + 3 + FPS * j;
             o[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
             o[1] = (float)urg;
             o[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
@@ -624,14 +652,6 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
                 }
             }
         }
-    }
-    __syncwarp();
-    const int n = 3 + FPS * h.N;
-    constexpr int kIters = (3 + FPS * 32 * SPL + 31) / 32;
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-        const int i = lane + 32 * it;
-        if (i < n) out[i] = stage[i];
     }
 }
 
@@ -900,7 +920,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     StepDraws<Real, SPL> sd;
     dr.generate(lane, false, sd);
     float* out = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, SPL, FPS>(p, h, s, sd, lane, ws.obs, out);
+    observe<Real, SPL, FPS>(p, h, s, sd, lane, out);
     for (int i = 3 + FPS * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
     const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
     __syncwarp();
@@ -1188,6 +1208,22 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks environments e = warp_id, warp_id + total_warps, ...
+// uav_env.py:481-485 + reward_function.py:59-67: -5000 per unvisited sensor, -1000 per sensor whose collection
+// ratio is under 20 %.  Out of line: it runs once per episode.
+template <typename Real, int SPL>
+__device__ __noinline__ Real terminal_penalties(const Params<Real>& p, Real reward, int N, uint32_t vis_lo, uint32_t vis_hi,
+                                                const Real (&tx)[SPL], const Real (&gen)[SPL]) {
+    const int unvisited = N - (__popc(vis_lo) + __popc(vis_hi));
+    if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
+    int starved = 0;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k)
+        starved += __popc(__ballot_sync(kFull, gen[k] > Real(0) && fdiv(tx[k], gen[k]) < p.cr_thr));
+    Real pen = Real(0);
+    for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
+    return reward + pen;
+}
+
 // Episode end inside a step (SB3 VecEnv semantics): terminal observation, episode statistics, new episode.
 // Deliberately NOT inlined and self-contained -- it re-reads the sensor columns the step has just stored
 // -- so that the rare path costs the hot loop neither registers nor local memory.
@@ -1198,7 +1234,8 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
     if (b.terminal_obs) {
         const int n = 3 + FPS * N;
         float* t = b.terminal_obs + (size_t)e * p.obs_dim;
-        for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? ws.obs[i] : 0.0f;
+        const float* row = b.obs + (size_t)e * p.obs_stride;  // written by this warp a moment ago
+        for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? row[i] : 0.0f;
     }
     Sensor<Real> s[SPL];
     load_sensors<Real, SPL>(b, p, e, N, lane, s);
@@ -1326,22 +1363,18 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         if (!(h.battery > p.batt_floor)) truncated = true;  // uav.py:224
         if (h.step >= p.max_steps) truncated = true;
         if (truncated) {
-            const int unvisited = N - (__popc(h.vis_lo) + __popc(h.vis_hi));
-            if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
-            int starved = 0;  // reward_function.py:59-67
+            Real txv[SPL], genv[SPL];
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
-                const Real g = generated_of(p, s[k], h.elapsed);
-                starved += __popc(__ballot_sync(kFull, s[k].active && g > Real(0) && fdiv(s[k].tx, g) < p.cr_thr));
+                txv[k] = s[k].active ? s[k].tx : Real(0);
+                genv[k] = s[k].active ? generated_of(p, s[k], h.elapsed) : Real(0);
             }
-            Real pen = Real(0);
-            for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
-            reward += pen;
+            reward = terminal_penalties<Real, SPL>(p, reward, N, h.vis_lo, h.vis_hi, txv, genv);
         }
 
         // ---- observation (uav_env.py:638-674) ----
         float* obs_row = b.obs + (size_t)e * p.obs_stride;
-        observe<Real, SPL, FPS>(p, h, s, sd, lane, ws.obs, obs_row);
+        observe<Real, SPL, FPS>(p, h, s, sd, lane, obs_row);
 
         // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
         Real shaped = reward;

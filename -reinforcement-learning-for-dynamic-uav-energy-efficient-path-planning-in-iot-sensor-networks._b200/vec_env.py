@@ -149,7 +149,8 @@ class UAVVecEnv:
                             _ptr(self.episode_stats), _ptr(self.action_mask), _ptr(self.step_detail),
                             _ptr(self.draw_export))
             N.check(self.lib.uavsim_bind_outputs(self._h, C.byref(out), self._stream()))
-            self._fields = {f: self._field_tensor(f) for f in range(5)}
+            n_fields = 5 if precision == "f64" else 4      # f32: SF is packed into avg_rssi
+            self._fields = {f: self._field_tensor(f) for f in range(n_fields)}
             sums = C.c_void_p()
             N.check(self.lib.uavsim_stat_sums(self._h, C.byref(sums)))
             off = sums.value - self._arena.data_ptr()
@@ -307,11 +308,18 @@ class UAVVecEnv:
         return int(self.lib.uavsim_launch_count(self._h))
 
     def state(self) -> dict:
-        """Zero-copy views of the structure-of-arrays state in HBM."""
+        """Views of the structure-of-arrays state in HBM (zero-copy, except that in the float32
+        layout the spreading factor is decoded from the three low mantissa bits of avg_rssi)."""
         st = self._fields[N.FIELD_SENSOR_STATE]
+        if self.precision == "f64":
+            avg, sf = st[..., 3], self._fields[N.FIELD_SENSOR_SF]
+        else:
+            bits = st[..., 3].contiguous().view(torch.int32)
+            sf = ((bits & 7) + 7).to(torch.uint8)
+            avg = (bits & ~7).view(torch.float32)
         return dict(records=self._fields[N.FIELD_ENV_RECORD], buffer=st[..., 0], transmitted=st[..., 1],
-                    lost=st[..., 2], avg_rssi=st[..., 3], sensor_pos=self._fields[N.FIELD_SENSOR_POS],
-                    generated_base=self._fields[N.FIELD_SENSOR_GEN], spreading_factor=self._fields[N.FIELD_SENSOR_SF])
+                    lost=st[..., 2], avg_rssi=avg, sensor_pos=self._fields[N.FIELD_SENSOR_POS],
+                    generated_base=self._fields[N.FIELD_SENSOR_GEN], spreading_factor=sf)
 
     def records(self) -> np.ndarray:
         """Host copy of the per-env records as a numpy structured array (uavsim_env_record)."""

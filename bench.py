@@ -51,7 +51,8 @@ def bytes_per_env_step(n_sensors: int, precision: str = "f32", obs_floats: int |
     per_sensor = 4 * rb * 2          # {buffer, transmitted, lost, avg_rssi} read + write
     per_sensor += 8                  # position float2, read
     per_sensor += rb if precision == "f32" else 2 * rb   # generated: f32 reads the reset value; f64 accumulates r+w
-    per_sensor += 2                  # spreading factor u8 read + write
+    if precision != "f32":
+        per_sensor += 2              # spreading factor u8 read + write (f32: packed into avg_rssi)
     per_env = 128 * 2                # env record read + write
     per_env += 4                     # action int32
     per_env += 4 * (obs_floats if obs_floats is not None else 3 + 3 * n_sensors)   # observation row

@@ -1206,6 +1206,92 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
     out.win_mask = win_mask;
 }
 
+// ------------------------------------------------------------------------------------------------
+// software pipeline of the throughput build: while a warp computes environment i, the columns of its
+// next environment (i + total_warps) stream from HBM into a shared-memory stage with cp.async
+// (LDGSTS: no registers held, no stall until the data is needed), double buffered per warp.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int SPL>
+struct alignas(16) StageBuf {
+    SensorState<Real> st[32 * SPL];
+    float2 pos[32 * SPL];
+    Real gen[32 * SPL];
+    uavsim_env_record rec;
+    int32_t action;
+    int32_t pad[3];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// Issue the asynchronous copies of environment e (N real sensors) into a stage buffer.
+template <typename Real, int SPL>
+__device__ __forceinline__ void stage_issue(const Buffers& b, const Params<Real>& p, const int32_t* actions, int e, int N,
+                                            int lane, StageBuf<Real, SPL>& sb) {
+    static_assert(sizeof(SensorState<Real>) == 16, "the staged pipeline is built for the float32 layout");
+    const uint32_t row = (uint32_t)e * (uint32_t)p.P;
+    const SensorState<Real>* st = reinterpret_cast<const SensorState<Real>*>(b.sstate);
+    const Real* gen = reinterpret_cast<const Real*>(b.sgen);
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < N) {
+            const uint32_t i = row + (uint32_t)j;
+            cp_async16(&sb.st[j], st + i);
+            cp_async8(&sb.pos[j], b.spos + i);
+            cp_async4(&sb.gen[j], gen + i);
+        }
+    }
+    if (lane < 8) cp_async16(reinterpret_cast<uint4*>(&sb.rec) + lane, reinterpret_cast<const uint4*>(b.rec + e) + lane);
+    if (lane == 8) cp_async4(&sb.action, actions + e);
+}
+
+template <typename Real, int SPL>
+__device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& sb, int N, int lane, Sensor<Real> (&s)[SPL]) {
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        s[k].active = j < N;
+        s[k].attempt = false;
+        s[k].det = Real(0);
+        s[k].cur = Real(0);
+        SensorState<Real> v;
+        v.buf = v.tx = v.lost = Real(0);
+        v.ema = Real(CUDART_NAN);
+        float2 xy = make_float2(0.f, 0.f);
+        Real g = Real(0);
+        if (s[k].active) {
+            v = sb.st[j];
+            xy = sb.pos[j];
+            g = sb.gen[j];
+        }
+        float ema;
+        int sf;
+        unpack_sf(v.ema, ema, sf);
+        if (!s[k].active) sf = 12;
+        s[k].buf = v.buf;
+        s[k].tx = v.tx;
+        s[k].lost = v.lost;
+        s[k].ema = ema;
+        s[k].gen = g;
+        s[k].sx = xy.x;
+        s[k].sy = xy.y;
+        s[k].sf = sf;
+    }
+}
+
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks environments e = warp_id, warp_id + total_warps, ...
 // uav_env.py:481-485 + reward_function.py:59-67: -5000 per unvisited sensor, -1000 per sensor whose collection
@@ -1249,22 +1335,63 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
     __shared__ WarpSmem smem[kWarpsPerBlock];
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
+    __shared__ StageBuf<float, SPL> stage[kStaged ? kWarpsPerBlock : 1][kStaged ? 2 : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem& ws = smem[warp];
     uavsim_env_record& R = ws.rec;
-    constexpr bool kParity = std::is_same<Real, double>::value;
-
-    for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
-        const int action = actions[e];
-        if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
-            if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
-            continue;
+    const int stride = gridDim.x * kWarpsPerBlock;
+    int e = blockIdx.x * kWarpsPerBlock + warp;
+    int cur = 0, n_next = 0;
+    if constexpr (kStaged) {
+        if (e < b.E) {
+            const int n0 = b.rec[e].num_sensors;
+            stage_issue<Real, SPL>(b, p, actions, e, n0, lane, reinterpret_cast<StageBuf<Real, SPL>&>(stage[warp][0]));
         }
-        load_record(ws, b.rec + e, lane);
-        Hot h = read_hot(R);
-        const int N = h.N;
+        cp_async_commit();
+        if (e + stride < b.E) n_next = b.rec[e + stride].num_sensors;
+    }
+
+    for (; e < b.E; e += stride) {
+        int action;
+        Hot h;
         Sensor<Real> s[SPL];
-        load_sensors<Real, SPL>(b, p, e, N, lane, s);
+        if constexpr (kStaged) {
+            // launch the copies of the NEXT environment, fetch the sensor count of the one after that,
+            // then wait for the CURRENT environment's stage (issued one iteration ago)
+            const int e1 = e + stride, e2 = e1 + stride;
+            if (e1 < b.E)
+                stage_issue<Real, SPL>(b, p, actions, e1, n_next, lane,
+                                       reinterpret_cast<StageBuf<Real, SPL>&>(stage[warp][cur ^ 1]));
+            cp_async_commit();
+            int n_next2 = 0;
+            if (e2 < b.E) n_next2 = b.rec[e2].num_sensors;
+            cp_async_wait<1>();
+            __syncwarp();
+            const StageBuf<Real, SPL>& sb = reinterpret_cast<const StageBuf<Real, SPL>&>(stage[warp][cur]);
+            action = sb.action;
+            reinterpret_cast<uint32_t*>(&R)[lane] = reinterpret_cast<const uint32_t*>(&sb.rec)[lane];
+            load_sensors_staged<Real, SPL>(sb, sb.rec.num_sensors, lane, s);
+            __syncwarp();
+            cur ^= 1;
+            n_next = n_next2;
+            if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
+                if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+                continue;
+            }
+            h = read_hot(R);
+        } else {
+            action = actions[e];
+            if (action < 0 || action > 4) {
+                if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+                continue;
+            }
+            load_record(ws, b.rec + e, lane);
+            h = read_hot(R);
+            load_sensors<Real, SPL>(b, p, e, h.N, lane, s);
+        }
+        const int N = h.N;
 
         // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
         h.step += 1;
@@ -1463,6 +1590,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         store_sensors<Real, SPL>(b, p, e, lane, s, false);
         if (restart) finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
         store_record(ws, b.rec + e, lane);
+        __syncwarp();
     }
 }
 

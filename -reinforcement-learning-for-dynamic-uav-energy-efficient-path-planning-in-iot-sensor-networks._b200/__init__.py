@@ -9,6 +9,8 @@ from ._native import UavsimError  # noqa: F401
 
 _native.load()  # fail loudly at import time if the CUDA library is missing
 
+from .sharding import allreduce_episode_stats, make_sharded_env, shard_range  # noqa: E402,F401
 from .vec_env import CURRICULUM_STAGES, MAX_SENSORS_LIMIT, UAVVecEnv  # noqa: E402,F401
 
-__all__ = ["UAVVecEnv", "UavsimError", "CURRICULUM_STAGES", "MAX_SENSORS_LIMIT"]
+__all__ = ["UAVVecEnv", "UavsimError", "CURRICULUM_STAGES", "MAX_SENSORS_LIMIT", "shard_range",
+           "make_sharded_env", "allreduce_episode_stats"]

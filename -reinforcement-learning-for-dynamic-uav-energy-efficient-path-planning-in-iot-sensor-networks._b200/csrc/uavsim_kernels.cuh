@@ -36,6 +36,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <cstddef>
 #include <type_traits>
 
 #include "philox.cuh"
@@ -354,92 +355,94 @@ __device__ __forceinline__ Real u01(uint32_t a) {
         return fminf(fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
 }
 
-// All draws one step makes on this lane's sensor slots, produced up front.
-template <typename Real, int SPL>
-struct StepDraws {
-    Real d[SPL], e[SPL];           // observation: ADR draw, range draw      (uav_env.py:654-660)
-    Real a[SPL], b[SPL], u[SPL];   // collect: ADR draw, link draw, uniform  (uav_env.py:535-551)
-};
-
+// Draws of one environment-step.  Two views, generated where they are consumed so that they are not
+// live across the whole step:
+//   obs(lane, d, e)        D (ADR) and E (range check) of the observation pass   uav_env.py:654-660
+//   collect(lane, a, b, u) A (ADR), B (link probability), U (duty-cycle uniform) uav_env.py:535-551
+//   winner(lane, k)        C, the range check of an SF-group winner              iot_sensors.py:131-133
 // REPLAY: slot-addressed table [6][P] of this environment.
-// PHILOX: counter = (env id, stream | env hi, episode, step << 8 | lane << 3 | call).  One Philox4x32-10
-// call yields four words = two Box-Muller pairs, so with two sensor slots per lane a MOVE step costs ONE
-// call per lane (D,E for both slots) and a COLLECT step three (+ D,E | A,B | U,U); with one slot per lane
-// one and two.  The winner's range-check draw C is generated lazily by the owning lane (call 4 + slot).
+// PHILOX: counter = (env id, stream | env hi, episode, step << 8 | lane << 3 | call), key = seed.  One
+// Philox4x32-10 call yields four words = two Box-Muller pairs:
+//   call 0: D,E of slot 0 (x,y) and of slot 1 (z,w)          -> a MOVE step costs ONE call per lane
+//   call 1: A,B of slot 0 (x,y) and of slot 1 (z,w); with one slot per lane U = z
+//   call 2: U of slot 0 (x) and slot 1 (y)                   (two slots per lane only)
+//   call 4+k: C of slot k (x,y), generated lazily by the owning lane
 template <typename Real, bool REPLAY, int SPL>
 struct Draws {
-    const double* tab;
-    Real* exp;  // optional export of the draws actually used, [6][P]
-    int P;
-    uint32_t k0, k1, env_lo, env_hi, episode, step;
-    Real sigma;
+    const double* tab;  // replay table of this environment (REPLAY only)
+    Real* exp;          // optional export of the draws actually used, [6][P]
+    uint32_t env_lo, env_hi, episode, step;
 
-    __device__ __forceinline__ Philox4 call(int lane, uint32_t c) const {
-        return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c, k0, k1);
+    __device__ __forceinline__ Philox4 call(const Params<Real>& p, int lane, uint32_t c) const {
+        return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c,
+                             p.key0, p.key1);
     }
-    __device__ __forceinline__ void put(int slot, int j, Real v) const {
-        if (exp && j < P) exp[slot * P + j] = v;
+    __device__ __forceinline__ void put(const Params<Real>& p, int slot, int j, Real v) const {
+        if (exp && j < p.P) exp[slot * p.P + j] = v;
     }
-    __device__ __forceinline__ void generate(int lane, bool collect, StepDraws<Real, SPL>& o) const {
+    __device__ __forceinline__ void obs(const Params<Real>& p, int lane, Real (&d)[SPL], Real (&e)[SPL]) const {
         if constexpr (REPLAY) {
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 const int j = lane + 32 * k;
-                const bool in = j < P;
-                o.d[k] = in ? (Real)tab[UAVSIM_SLOT_D * P + j] : Real(0);
-                o.e[k] = in ? (Real)tab[UAVSIM_SLOT_E * P + j] : Real(0);
-                o.a[k] = o.b[k] = o.u[k] = Real(0);
-                if (collect && in) {
-                    o.a[k] = (Real)tab[UAVSIM_SLOT_A * P + j];
-                    o.b[k] = (Real)tab[UAVSIM_SLOT_B * P + j];
-                    o.u[k] = (Real)tab[UAVSIM_SLOT_U * P + j];
-                }
+                const bool in = j < p.P;
+                d[k] = in ? (Real)tab[UAVSIM_SLOT_D * p.P + j] : Real(0);
+                e[k] = in ? (Real)tab[UAVSIM_SLOT_E * p.P + j] : Real(0);
             }
         } else {
-            const Philox4 q0 = call(lane, 0);
-            box_muller<Real>(q0.x, q0.y, sigma, o.d[0], o.e[0]);
-            if constexpr (SPL == 2) box_muller<Real>(q0.z, q0.w, sigma, o.d[1], o.e[1]);
-#pragma unroll
-            for (int k = 0; k < SPL; ++k) o.a[k] = o.b[k] = o.u[k] = Real(0);
-            if (collect) {
-                if constexpr (SPL == 1) {
-                    box_muller<Real>(q0.z, q0.w, sigma, o.a[0], o.b[0]);
-                    const Philox4 q1 = call(lane, 1);
-                    o.u[0] = u01<Real>(q1.x);
-                } else {
-                    const Philox4 q1 = call(lane, 1);
-                    box_muller<Real>(q1.x, q1.y, sigma, o.a[0], o.b[0]);
-                    box_muller<Real>(q1.z, q1.w, sigma, o.a[1], o.b[1]);
-                    const Philox4 q2 = call(lane, 2);
-                    o.u[0] = u01<Real>(q2.x);
-                    o.u[1] = u01<Real>(q2.y);
-                }
-            }
+            const Philox4 q0 = call(p, lane, 0);
+            box_muller<Real>(q0.x, q0.y, p.sigma, d[0], e[0]);
+            if constexpr (SPL == 2) box_muller<Real>(q0.z, q0.w, p.sigma, d[1], e[1]);
             if (exp) {
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) {
-                    const int j = lane + 32 * k;
-                    put(UAVSIM_SLOT_D, j, o.d[k]);
-                    put(UAVSIM_SLOT_E, j, o.e[k]);
-                    if (collect) {
-                        put(UAVSIM_SLOT_A, j, o.a[k]);
-                        put(UAVSIM_SLOT_B, j, o.b[k]);
-                        put(UAVSIM_SLOT_U, j, o.u[k]);
-                    }
+                    put(p, UAVSIM_SLOT_D, lane + 32 * k, d[k]);
+                    put(p, UAVSIM_SLOT_E, lane + 32 * k, e[k]);
                 }
             }
         }
     }
-    // winner's range-check draw C: iot_sensors.py:131-133 via uav_env.py:581 (called by the owner lane only)
-    __device__ __forceinline__ Real winner_draw(int lane, int k) const {
+    __device__ __forceinline__ void collect(const Params<Real>& p, int lane, Real (&a)[SPL], Real (&b)[SPL],
+                                            Real (&u)[SPL]) const {
+        if constexpr (REPLAY) {
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                const bool in = j < p.P;
+                a[k] = in ? (Real)tab[UAVSIM_SLOT_A * p.P + j] : Real(0);
+                b[k] = in ? (Real)tab[UAVSIM_SLOT_B * p.P + j] : Real(0);
+                u[k] = in ? (Real)tab[UAVSIM_SLOT_U * p.P + j] : Real(1);
+            }
+        } else {
+            const Philox4 q1 = call(p, lane, 1);
+            box_muller<Real>(q1.x, q1.y, p.sigma, a[0], b[0]);
+            if constexpr (SPL == 1) {
+                u[0] = u01<Real>(q1.z);
+            } else {
+                box_muller<Real>(q1.z, q1.w, p.sigma, a[1], b[1]);
+                const Philox4 q2 = call(p, lane, 2);
+                u[0] = u01<Real>(q2.x);
+                u[1] = u01<Real>(q2.y);
+            }
+            if (exp) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    put(p, UAVSIM_SLOT_A, lane + 32 * k, a[k]);
+                    put(p, UAVSIM_SLOT_B, lane + 32 * k, b[k]);
+                    put(p, UAVSIM_SLOT_U, lane + 32 * k, u[k]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ Real winner(const Params<Real>& p, int lane, int k) const {
         const int j = lane + 32 * k;
         if constexpr (REPLAY) {
-            return (Real)tab[UAVSIM_SLOT_C * P + j];
+            return (Real)tab[UAVSIM_SLOT_C * p.P + j];
         } else {
-            const Philox4 q = call(lane, 4u + (uint32_t)k);
+            const Philox4 q = call(p, lane, 4u + (uint32_t)k);
             Real c, unused;
-            box_muller<Real>(q.x, q.y, sigma, c, unused);
-            put(UAVSIM_SLOT_C, j, c);
+            box_muller<Real>(q.x, q.y, p.sigma, c, unused);
+            put(p, UAVSIM_SLOT_C, j, c);
             return c;
         }
     }
@@ -611,16 +614,18 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 // into the row (the partial sectors of neighbouring lanes merge in L2; DRAM sees the row once); ghost
 // slots are zero-filled when the buffer is bound / an episode starts and never touched by a step (N is
 // fixed during an episode).
-template <typename Real, int SPL, int FPS>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool HEAD>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
-                                        const StepDraws<Real, SPL>& sd, int lane, float* __restrict__ out) {
+                                        const Draws<Real, REPLAY, SPL>& dr, int lane, float* __restrict__ out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
+    Real dd[SPL], de[SPL];
+    dr.obs(p, lane, dd, de);
     float inv_w = 0.f, inv_h = 0.f;
     if constexpr (!kParity && FPS == 5) {
         inv_w = fast_rcp((float)h.W);
         inv_h = fast_rcp((float)h.H);
     }
-    if (lane == 0) {
+    if (HEAD && lane == 0) {  // the step writes these three in its per-lane phase C
         if constexpr (kParity) {
             out[0] = (float)((double)h.x / (double)h.W);
             out[1] = (float)((double)h.y / (double)h.H);
@@ -635,8 +640,8 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
         const Real urg = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], h.elapsed));
-        adr_update(p, s[k].det + sd.d[k], s[k].ema, s[k].sf);
-        const bool in_range = (s[k].det + sd.e[k]) >= p.thr;
+        adr_update(p, s[k].det + dd[k], s[k].ema, s[k].sf);
+        const bool in_range = (s[k].det + de[k]) >= p.thr;
         if (s[k].active) {
             float* o = out + 3 + FPS * j;
             o[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
@@ -907,20 +912,14 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     h.episode = episode;
     compute_det(p, h.x, h.y, s);
     Draws<Real, REPLAY, SPL> dr;
-    dr.P = p.P;
-    dr.sigma = p.sigma;
-    dr.k0 = p.key0;
-    dr.k1 = p.key1;
     dr.env_lo = env_lo;
     dr.env_hi = env_hi;
     dr.episode = episode;
     dr.step = 0;
     dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = exp;
-    StepDraws<Real, SPL> sd;
-    dr.generate(lane, false, sd);
     float* out = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, SPL, FPS>(p, h, s, sd, lane, out);
+    observe<Real, REPLAY, SPL, FPS, true>(p, h, s, dr, lane, out);
     for (int i = 3 + FPS * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
     const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
     __syncwarp();
@@ -1011,8 +1010,8 @@ struct CollectOut {
 // UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment.
 template <typename Real, bool REPLAY, int SPL>
 __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Sensor<Real> (&s)[SPL],
-                                               const StepDraws<Real, SPL>& sd, const Draws<Real, REPLAY, SPL>& dr,
-                                               Real step_loss, int lane, WarpSmem& ws, CollectOut<Real>& out) {
+                                               const Draws<Real, REPLAY, SPL>& dr, Real step_loss, int lane,
+                                               WarpSmem& ws, CollectOut<Real>& out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     const int N = h.N;
     float before[SPL];
@@ -1021,14 +1020,16 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
     h.battery -= p.e_hover;                                                    // uav.py:205
     const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
     // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
+    Real da[SPL], db[SPL], du[SPL];
+    dr.collect(p, lane, da, db, du);
     unsigned att[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         bool a = false;
         if (s[k].active && s[k].buf > Real(0)) {
-            s[k].cur = s[k].det + sd.a[k];
+            s[k].cur = s[k].det + da[k];
             adr_update(p, s[k].cur, s[k].ema, s[k].sf);
-            const Real rb = s[k].det + sd.b[k];
+            const Real rb = s[k].det + db[k];
             Real plink;
             if (rb < p.thr) {
                 plink = Real(0);
@@ -1039,7 +1040,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
                 else
                     plink = __fdividef(1.0f, 1.0f + __expf(-x));
             }
-            a = (plink * p.duty_frac) > sd.u[k];
+            a = (plink * p.duty_frac) > du[k];
         }
         s[k].attempt = a;
         att[k] = __ballot_sync(kFull, a);
@@ -1111,7 +1112,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
                 if (lane + 32 * k == winner) {
-                    const Real rc = s[k].det + dr.winner_draw(lane, k);
+                    const Real rc = s[k].det + dr.winner(p, lane, k);
                     in_range = rc >= p.thr;
                     if (in_range && s[k].buf > Real(0)) {
                         const Real cap = data_rate_of<Real>(s[k].sf) * p.cd;
@@ -1216,9 +1217,6 @@ struct alignas(16) StageBuf {
     SensorState<Real> st[32 * SPL];
     float2 pos[32 * SPL];
     Real gen[32 * SPL];
-    uavsim_env_record rec;
-    int32_t action;
-    int32_t pad[3];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
@@ -1238,8 +1236,8 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // Issue the asynchronous copies of environment e (N real sensors) into a stage buffer.
 template <typename Real, int SPL>
-__device__ __forceinline__ void stage_issue(const Buffers& b, const Params<Real>& p, const int32_t* actions, int e, int N,
-                                            int lane, StageBuf<Real, SPL>& sb) {
+__device__ __forceinline__ void stage_issue(const Buffers& b, const Params<Real>& p, int e, int N, int lane,
+                                            StageBuf<Real, SPL>& sb) {
     static_assert(sizeof(SensorState<Real>) == 16, "the staged pipeline is built for the float32 layout");
     const uint32_t row = (uint32_t)e * (uint32_t)p.P;
     const SensorState<Real>* st = reinterpret_cast<const SensorState<Real>*>(b.sstate);
@@ -1254,8 +1252,6 @@ __device__ __forceinline__ void stage_issue(const Buffers& b, const Params<Real>
             cp_async4(&sb.gen[j], gen + i);
         }
     }
-    if (lane < 8) cp_async16(reinterpret_cast<uint4*>(&sb.rec) + lane, reinterpret_cast<const uint4*>(b.rec + e) + lane);
-    if (lane == 8) cp_async4(&sb.action, actions + e);
 }
 
 template <typename Real, int SPL>
@@ -1292,24 +1288,6 @@ __device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& s
     }
 }
 
-// One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
-// full residency and each warp walks environments e = warp_id, warp_id + total_warps, ...
-// uav_env.py:481-485 + reward_function.py:59-67: -5000 per unvisited sensor, -1000 per sensor whose collection
-// ratio is under 20 %.  Out of line: it runs once per episode.
-template <typename Real, int SPL>
-__device__ __noinline__ Real terminal_penalties(const Params<Real>& p, Real reward, int N, uint32_t vis_lo, uint32_t vis_hi,
-                                                const Real (&tx)[SPL], const Real (&gen)[SPL]) {
-    const int unvisited = N - (__popc(vis_lo) + __popc(vis_hi));
-    if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
-    int starved = 0;
-#pragma unroll
-    for (int k = 0; k < SPL; ++k)
-        starved += __popc(__ballot_sync(kFull, gen[k] > Real(0) && fdiv(tx[k], gen[k]) < p.cr_thr));
-    Real pen = Real(0);
-    for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
-    return reward + pen;
-}
-
 // Episode end inside a step (SB3 VecEnv semantics): terminal observation, episode statistics, new episode.
 // Deliberately NOT inlined and self-contained -- it re-reads the sensor columns the step has just stored
 // -- so that the rare path costs the hot loop neither registers nor local memory.
@@ -1330,267 +1308,465 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
     store_sensors<Real, SPL>(b, p, e, lane, s, true);
 }
 
+// ------------------------------------------------------------------------------------------------
+// the step kernel: tiles of kTile consecutive environments per warp
+// ------------------------------------------------------------------------------------------------
+// Per-environment SCALAR work (action decode, UAV move + battery, edge bookkeeping, truncation, reward
+// assembly, terminal penalties, shaping, record update, reward/done/mask outputs) is identical for every
+// lane when a warp owns one environment -- 32 lanes would issue it to produce one result.  So a warp
+// takes a TILE of kTile environments and runs that work one-environment-per-LANE (phases A and C),
+// while the per-sensor work stays one-environment-per-WARP with sensors across lanes (phase B, a loop
+// over the tile).  The phases talk through a small structure-of-arrays block in shared memory; the tile's
+// 128-byte records sit in shared memory with a 4-byte XOR swizzle so that both the coalesced global
+// copies (lane = word) and the per-lane field accesses (lane = environment) are bank-conflict free.
+constexpr int kTile = 16;
+
+template <typename Real>
+struct alignas(16) TileSmem {
+    uint32_t rec[kTile][32];  // word w of record l lives at rec[l][w ^ l]
+    // phase A -> phase B (read as warp-wide broadcasts) and -> phase C
+    float x[kTile], y[kTile], elapsed[kTile];
+    int32_t N[kTile], W[kTile], H[kTile], step[kTile], flags[kTile];
+    uint32_t episode[kTile], vis_lo[kTile], vis_hi[kTile];
+    double battery[kTile];
+    Real used[kTile];
+    // phase B -> phase C
+    Real step_loss[kTile], creward[kTile], bytes[kTile], jain[kTile];
+    float cur_dist[kTile];
+    int32_t counts[kTile];  // collisions | captures << 8 | delivered << 12 | starved << 16
+    uint32_t nvis_lo[kTile], nvis_hi[kTile];
+};
+
+// Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
+// the tile block and (float32 layout) two stage buffers.
+template <typename Real, int SPL>
+struct alignas(16) StepWarpSmem {
+    WarpSmem ws;
+    TileSmem<Real> ts;
+    StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : 2];
+};
+template <typename Real, int SPL>
+constexpr size_t step_smem_bytes() {
+    return sizeof(StepWarpSmem<Real, SPL>) * kWarpsPerBlock;
+}
+
+enum : int {
+    kFlagValid = 1, kFlagCollect = 2, kFlagTruncated = 4, kFlagMoveOk = 8, kFlagEdge = 16, kFlagJain = 32
+};
+
+// record word offsets (uavsim_env_record, include/uavsim.h)
+enum : int {
+    kRX = 0, kRY = 1, kRStartX = 2, kRStartY = 3, kRBattery = 4, kRTotalReward = 6, kRTotalData = 8, kREpReturn = 10,
+    kRLastBytes = 12, kRPrevDist = 13, kRElapsed = 14, kRStep = 15, kRGridW = 16, kRGridH = 17, kRN = 18, kRVisLo = 19,
+    kRVisHi = 20, kRCapture = 21, kRBoundary = 22, kREdge = 23, kRCollisions = 24, kRFirstCov = 25, kREpisode = 26,
+    kRDelivered = 27
+};
+static_assert(offsetof(uavsim_env_record, battery) == 4 * kRBattery && offsetof(uavsim_env_record, step) == 4 * kRStep &&
+                  offsetof(uavsim_env_record, num_sensors) == 4 * kRN && offsetof(uavsim_env_record, episode) == 4 * kREpisode &&
+                  offsetof(uavsim_env_record, delivered) == 4 * kRDelivered && offsetof(uavsim_env_record, elapsed_s) == 4 * kRElapsed &&
+                  offsetof(uavsim_env_record, total_reward) == 4 * kRTotalReward && offsetof(uavsim_env_record, episode_return) == 4 * kREpReturn &&
+                  offsetof(uavsim_env_record, prev_dist_nearest) == 4 * kRPrevDist && offsetof(uavsim_env_record, first_full_coverage_step) == 4 * kRFirstCov,
+              "record word map out of date");
+
+struct RecView {  // lane-private access to record l of the swizzled tile
+    uint32_t* row;
+    int l;
+    __device__ __forceinline__ uint32_t& w(int i) const { return row[i ^ l]; }
+    __device__ __forceinline__ float f(int i) const { return __uint_as_float(row[i ^ l]); }
+    __device__ __forceinline__ int i32(int i) const { return (int)row[i ^ l]; }
+    __device__ __forceinline__ double d(int i) const { return __hiloint2double((int)row[(i + 1) ^ l], (int)row[i ^ l]); }
+    __device__ __forceinline__ void set_f(int i, float v) const { row[i ^ l] = __float_as_uint(v); }
+    __device__ __forceinline__ void set_i(int i, int v) const { row[i ^ l] = (uint32_t)v; }
+    __device__ __forceinline__ void set_d(int i, double v) const {
+        row[i ^ l] = (uint32_t)__double2loint(v);
+        row[(i + 1) ^ l] = (uint32_t)__double2hiint(v);
+    }
+};
+
+// Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.
+template <typename Real, bool REPLAY, int SPL, int FPS>
+__device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
+                                             int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    Hot h;
+    h.x = ts.x[k];
+    h.y = ts.y[k];
+    h.elapsed = ts.elapsed[k];
+    h.battery = 0.0;
+    h.W = ts.W[k];
+    h.H = ts.H[k];
+    h.N = ts.N[k];
+    h.step = ts.step[k];
+    h.vis_lo = ts.vis_lo[k];
+    h.vis_hi = ts.vis_hi[k];
+    h.episode = ts.episode[k];
+    h.prev_dist = 0.f;
+    const int flags = ts.flags[k];
+    const bool collect = flags & kFlagCollect;
+    const int N = h.N;
+    const Real dt = collect ? p.cd : Real(1);
+
+    const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+    Draws<Real, REPLAY, SPL> dr;
+    dr.env_lo = (uint32_t)gid;
+    dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
+    dr.episode = h.episode - 1;  // the record counts resets done; the running episode is one less
+    dr.step = (uint32_t)h.step;
+    dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
+    dr.exp = nullptr;
+    if (!REPLAY && b.draw_export) {
+        dr.exp = reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P;
+        const Real nan = Real(CUDART_NAN);
+        for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) dr.exp[i] = nan;
+        __syncwarp();
+    }
+
+    // ---- iot_sensors.py:114-125: age the buffers ----
+    Real loss[SPL];
+    const Real nw = p.rate * dt;
+    bool any_over = false;
+#pragma unroll
+    for (int k2 = 0; k2 < SPL; ++k2) {
+        if constexpr (kParity) s[k2].gen += nw;
+        const Real pot = s[k2].buf + nw;
+        const bool over = pot > p.maxbuf;
+        loss[k2] = over ? pot - p.maxbuf : Real(0);
+        s[k2].buf = over ? p.maxbuf : pot;
+        s[k2].lost += loss[k2];  // + 0 when not saturated: no effect on the stored value
+        any_over |= (s[k2].active && over);
+    }
+    Real step_loss = Real(0);
+    if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
+
+    compute_det(p, h.x, h.y, s);  // the UAV has already moved (phase A)
+    CollectOut<Real> co;
+    co.reward = co.total_bytes = co.urg_red = co.mean_urg = Real(0);
+    co.collisions = co.captures = co.delivered = 0;
+    co.any_new = co.was_empty = co.all_collected = false;
+    co.att_mask = co.win_mask = 0ull;
+    if (collect) collect_action<Real, REPLAY, SPL>(p, h, s, dr, step_loss, lane, ws, co);
+
+    int starved = 0;  // reward_function.py:59-67 (counted only when the episode ends this step)
+    if (flags & kFlagTruncated) {
+#pragma unroll
+        for (int k2 = 0; k2 < SPL; ++k2) {
+            const Real g = generated_of(p, s[k2], h.elapsed);
+            starved += __popc(__ballot_sync(kFull, s[k2].active && g > Real(0) && fdiv(s[k2].tx, g) < p.cr_thr));
+        }
+    }
+
+    // ---- observation, sensor part (uav_env.py:638-674); obs[0..2] are written by phase C ----
+    observe<Real, REPLAY, SPL, FPS, false>(p, h, s, dr, lane, b.obs + (size_t)e * p.obs_stride);
+
+    // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
+    float cur_dist = 0.f;
+    Real jain = Real(0);
+    bool have_jain = false;
+    if (p.domain_rand) {
+        cur_dist = nearest_with_data(h.x, h.y, s);
+        Real r1[SPL], r2[SPL];
+        int cnt = 0;
+#pragma unroll
+        for (int k2 = 0; k2 < SPL; ++k2) {
+            const Real g = generated_of(p, s[k2], h.elapsed);
+            const bool has = s[k2].active && g > Real(0);
+            const Real rate = has ? fdiv(s[k2].tx, g) * Real(100) : Real(0);
+            r1[k2] = rate;
+            r2[k2] = rate * rate;
+            cnt += __popc(__ballot_sync(kFull, has));
+        }
+        if (cnt > 0) {
+            const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
+            const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
+            jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
+            have_jain = true;
+        }
+    }
+    store_sensors<Real, SPL>(b, p, e, lane, s, false);
+
+    if (lane == 0) {
+        ts.step_loss[k] = step_loss;
+        ts.cur_dist[k] = cur_dist;
+        ts.jain[k] = jain;
+        if (have_jain) ts.flags[k] = flags | kFlagJain;
+        ts.counts[k] = starved << 16;
+        if (collect) {
+            ts.creward[k] = co.reward;
+            ts.bytes[k] = co.total_bytes;
+            ts.counts[k] = co.collisions | (co.captures << 8) | (co.delivered << 12) | (starved << 16);
+            ts.nvis_lo[k] = h.vis_lo;
+            ts.nvis_hi[k] = h.vis_hi;
+        }
+        if (b.step_detail) {  // parity diagnostics: the collect step's intermediates (phase C adds the rest)
+            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+            d[UAVSIM_DETAIL_COLLISIONS] = co.collisions;
+            d[UAVSIM_DETAIL_BYTES] = (double)co.total_bytes;
+            d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)co.urg_red;
+            d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)co.mean_urg;
+            d[UAVSIM_DETAIL_WAS_NEW] = co.any_new;
+            d[UAVSIM_DETAIL_WAS_EMPTY] = co.was_empty;
+            d[UAVSIM_DETAIL_ALL_COLLECTED] = co.all_collected;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)co.att_mask;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(co.att_mask >> 32);
+            d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)co.win_mask;
+            d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(co.win_mask >> 32);
+        }
+    }
+}
+
+// One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
+// full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
 template <typename Real, bool REPLAY, int SPL, int FPS>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
-    __shared__ WarpSmem smem[kWarpsPerBlock];
     constexpr bool kParity = std::is_same<Real, double>::value;
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
-    __shared__ StageBuf<float, SPL> stage[kStaged ? kWarpsPerBlock : 1][kStaged ? 2 : 1];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& ws = smem[warp];
-    uavsim_env_record& R = ws.rec;
-    const int stride = gridDim.x * kWarpsPerBlock;
-    int e = blockIdx.x * kWarpsPerBlock + warp;
-    int cur = 0, n_next = 0;
-    if constexpr (kStaged) {
-        if (e < b.E) {
-            const int n0 = b.rec[e].num_sensors;
-            stage_issue<Real, SPL>(b, p, actions, e, n0, lane, reinterpret_cast<StageBuf<Real, SPL>&>(stage[warp][0]));
-        }
+    StepWarpSmem<Real, SPL>& mine = reinterpret_cast<StepWarpSmem<Real, SPL>*>(dyn_smem)[warp];
+    WarpSmem& ws = mine.ws;
+    TileSmem<Real>& ts = mine.ts;
+    StageBuf<Real, SPL>* stage = mine.stage;
+    const int E = b.E;
+    const int tile_stride = gridDim.x * kWarpsPerBlock * kTile;
+    int base = (blockIdx.x * kWarpsPerBlock + warp) * kTile;
+    int cur = 0;
+    if constexpr (kStaged) {  // prime the pipeline with the first environment of the first tile
+        if (base < E)
+            stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane,
+                                   stage[0]);
         cp_async_commit();
-        if (e + stride < b.E) n_next = b.rec[e + stride].num_sensors;
     }
 
-    for (; e < b.E; e += stride) {
-        int action;
-        Hot h;
-        Sensor<Real> s[SPL];
-        if constexpr (kStaged) {
-            // launch the copies of the NEXT environment, fetch the sensor count of the one after that,
-            // then wait for the CURRENT environment's stage (issued one iteration ago)
-            const int e1 = e + stride, e2 = e1 + stride;
-            if (e1 < b.E)
-                stage_issue<Real, SPL>(b, p, actions, e1, n_next, lane,
-                                       reinterpret_cast<StageBuf<Real, SPL>&>(stage[warp][cur ^ 1]));
-            cp_async_commit();
-            int n_next2 = 0;
-            if (e2 < b.E) n_next2 = b.rec[e2].num_sensors;
-            cp_async_wait<1>();
-            __syncwarp();
-            const StageBuf<Real, SPL>& sb = reinterpret_cast<const StageBuf<Real, SPL>&>(stage[warp][cur]);
-            action = sb.action;
-            reinterpret_cast<uint32_t*>(&R)[lane] = reinterpret_cast<const uint32_t*>(&sb.rec)[lane];
-            load_sensors_staged<Real, SPL>(sb, sb.rec.num_sensors, lane, s);
-            __syncwarp();
-            cur ^= 1;
-            n_next = n_next2;
-            if (action < 0 || action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
-                if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
-                continue;
-            }
-            h = read_hot(R);
-        } else {
-            action = actions[e];
-            if (action < 0 || action > 4) {
-                if (lane == 0) atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
-                continue;
-            }
-            load_record(ws, b.rec + e, lane);
-            h = read_hot(R);
-            load_sensors<Real, SPL>(b, p, e, h.N, lane, s);
-        }
-        const int N = h.N;
+    for (; base < E; base += tile_stride) {
+        const int ntile = min(kTile, E - base);
+        // sensor count of the first environment of this warp's NEXT tile (needed to stage it)
+        int n_first_next = 0;
+        if (kStaged && base + tile_stride < E) n_first_next = b.rec[base + tile_stride].num_sensors;
 
-        // ---- uav_env.py:439-447: step counter, edge-cell bookkeeping (pre-move position) ----
-        h.step += 1;
-        int edge_delta = 0;
-        if constexpr (kParity) {
-            const double W = h.W, H = h.H, ux = h.x, uy = h.y, eps = 1e-6;
-            if (ux <= eps || uy <= eps || ux >= W - 1 - eps || uy >= H - 1 - eps) edge_delta = 1;
-        } else {
-            const float eps = 1e-6f;
-            if (h.x <= eps || h.y <= eps || h.x >= (float)(h.W - 1) - eps || h.y >= (float)(h.H - 1) - eps) edge_delta = 1;
-        }
-        const bool collect = action == 4;
-        const Real dt = collect ? p.cd : Real(1);
-        h.elapsed += (float)dt;
-
-        const uint64_t gid = (uint64_t)(p.env_id_offset + e);
-        Draws<Real, REPLAY, SPL> dr;
-        dr.P = p.P;
-        dr.sigma = p.sigma;
-        dr.k0 = p.key0;
-        dr.k1 = p.key1;
-        dr.env_lo = (uint32_t)gid;
-        dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
-        dr.episode = h.episode - 1;  // R.episode counts resets done; the running episode is one less
-        dr.step = (uint32_t)h.step;
-        dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-        dr.exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-        if (!REPLAY && dr.exp) {
-            const Real nan = Real(CUDART_NAN);
-            for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) dr.exp[i] = nan;
-            __syncwarp();
-        }
-        StepDraws<Real, SPL> sd;
-        dr.generate(lane, collect, sd);
-
-        // ---- iot_sensors.py:114-125: age the buffers ----
-        Real loss[SPL];
-        const Real nw = p.rate * dt;
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            if constexpr (kParity) s[k].gen += nw;
-            const Real pot = s[k].buf + nw;
-            const bool over = pot > p.maxbuf;
-            loss[k] = over ? pot - p.maxbuf : Real(0);
-            s[k].buf = over ? p.maxbuf : pot;
-            s[k].lost += loss[k];  // + 0 when not saturated: no effect on the stored value
-        }
-        bool any_over = false;
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) any_over |= (s[k].active && loss[k] > Real(0));
-        Real step_loss = Real(0);
-        if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
-
-        Real reward;
-        CollectOut<Real> co;
-        co.total_bytes = co.urg_red = co.mean_urg = Real(0);
-        co.collisions = co.captures = co.delivered = 0;
-        co.any_new = co.was_empty = co.all_collected = false;
-        co.att_mask = co.win_mask = 0ull;
-        int boundary_delta = 0;
-        if (!collect) {
-            // ---- uav.py:127-185 + reward_function.py:69-79 + uav_env.py:494-516 ----
-            float nx = h.x, ny = h.y;
-            if (action == 0)
-                ny += 1.0f;
-            else if (action == 1)
-                ny -= 1.0f;
-            else if (action == 2)
-                nx -= 1.0f;
-            else
-                nx += 1.0f;
-            const double before = h.battery;
-            const bool ok = (0.f <= nx) && (nx < (float)h.W) && (0.f <= ny) && (ny < (float)h.H);
-            if (ok) {
-                h.x = nx;
-                h.y = ny;
-                h.battery -= p.e_move;
-            } else {
-                h.battery -= p.e_fail;
-                boundary_delta = 1;
-            }
-            const Real used = (Real)(before - h.battery);
-            reward = p.p_step;
-            reward += ok ? p.r_move : p.p_boundary;
-            reward += p.p_battery * used;
-            reward += p.p_data_loss * step_loss;
-            compute_det(p, h.x, h.y, s);  // for the observation at the new position
-        } else {
-            compute_det(p, h.x, h.y, s);
-            collect_action<Real, REPLAY, SPL>(p, h, s, sd, dr, step_loss, lane, ws, co);
-            reward = co.reward;
-        }
-
-        // ---- uav_env.py:471-485: truncation + terminal penalties ----
-        bool truncated = false;
-        if (!(h.battery > p.batt_floor)) truncated = true;  // uav.py:224
-        if (h.step >= p.max_steps) truncated = true;
-        if (truncated) {
-            Real txv[SPL], genv[SPL];
-#pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                txv[k] = s[k].active ? s[k].tx : Real(0);
-                genv[k] = s[k].active ? generated_of(p, s[k], h.elapsed) : Real(0);
-            }
-            reward = terminal_penalties<Real, SPL>(p, reward, N, h.vis_lo, h.vis_hi, txv, genv);
-        }
-
-        // ---- observation (uav_env.py:638-674) ----
-        float* obs_row = b.obs + (size_t)e * p.obs_stride;
-        observe<Real, SPL, FPS>(p, h, s, sd, lane, obs_row);
-
-        // ---- DomainRandEnv.step shaping (dqn.py:415-444) ----
-        Real shaped = reward;
-        bool full_cov = false;
-        if (p.domain_rand) {
-            const float cur = nearest_with_data(h.x, h.y, s);
-            if (h.prev_dist > 0.f) {
-                if constexpr (kParity)
-                    shaped += p.prox_eta * ((double)h.prev_dist - (double)cur);
-                else
-                    shaped += p.prox_eta * (h.prev_dist - cur);
-            }
-            h.prev_dist = cur;
-            full_cov = (__popc(h.vis_lo) + __popc(h.vis_hi)) == N;
-            Real r1[SPL], r2[SPL];
-            int cnt = 0;
-#pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                const Real g = generated_of(p, s[k], h.elapsed);
-                const bool has = s[k].active && g > Real(0);
-                const Real rate = has ? fdiv(s[k].tx, g) * Real(100) : Real(0);
-                r1[k] = rate;
-                r2[k] = rate * rate;
-                cnt += __popc(__ballot_sync(kFull, has));
-            }
-            if (cnt > 0) {
-                const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
-                const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
-                const Real jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
-                shaped += fdiv(p.jain_bonus * (jain - Real(0.5)), (Real)N);
-            }
-        }
-
-        // ---- commit the record (lane 0) and write the per-env outputs ----
-        const bool restart = truncated && p.auto_reset;
-        if (lane == 0) {
-            if (!collect) {
-                R.x = h.x;
-                R.y = h.y;
-                if (boundary_delta) R.boundary_hits += 1;
-                if (R.last_step_bytes != 0.f) R.last_step_bytes = 0.f;
-            } else {
-                R.visited_lo = h.vis_lo;
-                R.visited_hi = h.vis_hi;
-                R.total_data_collected += (double)co.total_bytes;
-                R.last_step_bytes = (float)co.total_bytes;
-                R.capture_triggers += co.captures;
-                R.collisions += co.collisions;
-                R.delivered += co.delivered;
-            }
-            R.battery = h.battery;
-            R.elapsed_s = h.elapsed;
-            R.step = h.step;
-            R.total_reward += (double)reward;            // uav_env.py:487
-            R.episode_return += (double)shaped;
-            if (edge_delta) R.edge_steps += 1;
-            if (p.domain_rand) {
-                R.prev_dist_nearest = h.prev_dist;
-                if (full_cov && R.first_full_coverage_step < 0) R.first_full_coverage_step = h.step;
-            }
-            reinterpret_cast<Real*>(b.reward)[e] = shaped;
-            b.done[e] = truncated ? 1 : 0;
-            if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(h.x, h.y, h.W, h.H);
-            if (b.step_detail) {
-                double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
-                d[UAVSIM_DETAIL_COLLISIONS] = co.collisions;
-                d[UAVSIM_DETAIL_BYTES] = (double)co.total_bytes;
-                d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)co.urg_red;
-                d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)co.mean_urg;
-                d[UAVSIM_DETAIL_WAS_NEW] = co.any_new;
-                d[UAVSIM_DETAIL_WAS_EMPTY] = co.was_empty;
-                d[UAVSIM_DETAIL_ALL_COLLECTED] = co.all_collected;
-                d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
-                d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)co.att_mask;
-                d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(co.att_mask >> 32);
-                d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)co.win_mask;
-                d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(co.win_mask >> 32);
-                d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
-                d[UAVSIM_DETAIL_TRUNCATED] = truncated;
-                d[14] = 0.0;
-                d[15] = 0.0;
-            }
-        }
-
-        // ---- SB3 VecEnv semantics: finished episodes restart inside the same call ----
-        store_sensors<Real, SPL>(b, p, e, lane, s, false);
-        if (restart) finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
-        store_record(ws, b.rec + e, lane);
+        // ---- tile records: global -> swizzled shared memory (lane = word: coalesced 128-byte rows) ----
         __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kTile; ++r)
+            if (r < ntile) ts.rec[r][lane ^ r] = reinterpret_cast<const uint32_t*>(b.rec + base + r)[lane];
+        __syncwarp();
+
+        // ---- phase A: one environment per lane ----
+        const RecView R{ts.rec[lane & (kTile - 1)], lane & (kTile - 1)};
+        if (lane < ntile) {
+            const int e = base + lane;
+            int my_flags = 0;
+            const int my_action = actions[e];
+            if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
+                atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+            } else {
+                my_flags = kFlagValid;
+                float x = R.f(kRX), y = R.f(kRY);
+                const int W = R.i32(kRGridW), H = R.i32(kRGridH);
+                double battery = R.d(kRBattery);
+                const int step = R.i32(kRStep) + 1;  // uav_env.py:439
+                // uav_env.py:443-447: edge-cell bookkeeping on the PRE-move position
+                if constexpr (kParity) {
+                    const double Wd = W, Hd = H, ux = x, uy = y, eps = 1e-6;
+                    if (ux <= eps || uy <= eps || ux >= Wd - 1 - eps || uy >= Hd - 1 - eps) my_flags |= kFlagEdge;
+                } else {
+                    const float eps = 1e-6f;
+                    if (x <= eps || y <= eps || x >= (float)(W - 1) - eps || y >= (float)(H - 1) - eps) my_flags |= kFlagEdge;
+                }
+                const bool collect = my_action == 4;
+                Real used;
+                if (!collect) {  // uav.py:127-185
+                    float nx = x, ny = y;
+                    if (my_action == 0)
+                        ny += 1.0f;
+                    else if (my_action == 1)
+                        ny -= 1.0f;
+                    else if (my_action == 2)
+                        nx -= 1.0f;
+                    else
+                        nx += 1.0f;
+                    const double before = battery;
+                    const bool ok = (0.f <= nx) && (nx < (float)W) && (0.f <= ny) && (ny < (float)H);
+                    if (ok) {
+                        x = nx;
+                        y = ny;
+                        battery -= p.e_move;
+                        my_flags |= kFlagMoveOk;
+                    } else {
+                        battery -= p.e_fail;
+                    }
+                    used = (Real)(before - battery);
+                } else {  // uav.py:187-206, :260-263
+                    my_flags |= kFlagCollect;
+                    battery -= p.e_hover;
+                    used = (Real)p.used_hover;
+                }
+                if (!(battery > p.batt_floor) || step >= p.max_steps) my_flags |= kFlagTruncated;  // uav.py:224, uav_env.py:474-478
+                ts.x[lane] = x;
+                ts.y[lane] = y;
+                ts.elapsed[lane] = R.f(kRElapsed) + (float)(collect ? p.cd : Real(1));
+                ts.N[lane] = R.i32(kRN);
+                ts.W[lane] = W;
+                ts.H[lane] = H;
+                ts.step[lane] = step;
+                ts.episode[lane] = R.w(kREpisode);
+                ts.vis_lo[lane] = R.w(kRVisLo);
+                ts.vis_hi[lane] = R.w(kRVisHi);
+                ts.battery[lane] = battery;
+                ts.used[lane] = used;
+            }
+            ts.flags[lane] = my_flags;
+        }
+        __syncwarp();
+
+        // ---- phase B: one environment per warp, sensors across lanes ----
+        for (int k = 0; k < ntile; ++k) {
+            const int e = base + k;
+            Sensor<Real> s[SPL];
+            if constexpr (kStaged) {
+                // launch the copies of the NEXT environment of this warp's sequence, then wait for the
+                // CURRENT environment's stage (issued one iteration ago)
+                int e1 = e + 1, n1 = 0;
+                if (k + 1 < ntile) {
+                    n1 = (int)ts.rec[k + 1][kRN ^ (k + 1)];
+                } else {
+                    e1 = base + tile_stride;
+                    n1 = n_first_next;
+                }
+                if (e1 < E)
+                    stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[cur ^ 1]);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const bool valid = ts.flags[k] & kFlagValid;
+                if (valid)
+                    load_sensors_staged<Real, SPL>(stage[cur], ts.N[k], lane, s);
+                __syncwarp();
+                cur ^= 1;
+                if (!valid) continue;
+            } else {
+                if (!(ts.flags[k] & kFlagValid)) continue;
+                load_sensors<Real, SPL>(b, p, e, ts.N[k], lane, s);
+            }
+            sensor_phase<Real, REPLAY, SPL, FPS>(p, b, ts, ws, k, e, lane, s);
+        }
+        __syncwarp();
+
+        // ---- phase C: one environment per lane ----
+        unsigned restart_mask = 0u;
+        {
+            bool restart = false;
+            if (lane < ntile && (ts.flags[lane] & kFlagValid)) {
+                const int e = base + lane;
+                const int flags = ts.flags[lane];
+                const bool collect = flags & kFlagCollect, truncated = flags & kFlagTruncated;
+                const int N = ts.N[lane];
+                const Real step_loss = ts.step_loss[lane];
+                const int counts = ts.counts[lane];
+                Real reward, total_bytes = Real(0);
+                uint32_t vis_lo = ts.vis_lo[lane], vis_hi = ts.vis_hi[lane];
+                if (!collect) {  // reward_function.py:69-79 + uav_env.py:508-514
+                    reward = p.p_step;
+                    reward += (flags & kFlagMoveOk) ? p.r_move : p.p_boundary;
+                    reward += p.p_battery * ts.used[lane];
+                    reward += p.p_data_loss * step_loss;
+                } else {
+                    reward = ts.creward[lane];
+                    total_bytes = ts.bytes[lane];
+                    vis_lo = ts.nvis_lo[lane];
+                    vis_hi = ts.nvis_hi[lane];
+                }
+                if (truncated) {  // uav_env.py:481-485, reward_function.py:59-67
+                    const int unvisited = N - (__popc(vis_lo) + __popc(vis_hi));
+                    if (unvisited > 0) reward += p.p_unvisited * (Real)unvisited;
+                    const int starved = (counts >> 16) & 0xff;
+                    Real pen = Real(0);
+                    for (int i = 0; i < starved; ++i) pen += p.p_starved;  // the reference adds -1000 once per sensor
+                    reward += pen;
+                }
+                // DomainRandEnv.step shaping (dqn.py:415-444)
+                Real shaped = reward;
+                if (p.domain_rand) {
+                    const float prev = R.f(kRPrevDist), curd = ts.cur_dist[lane];
+                    if (prev > 0.f) {
+                        if constexpr (kParity)
+                            shaped += p.prox_eta * ((double)prev - (double)curd);
+                        else
+                            shaped += p.prox_eta * (prev - curd);
+                    }
+                    R.set_f(kRPrevDist, curd);
+                    if (R.i32(kRFirstCov) < 0 && (__popc(vis_lo) + __popc(vis_hi)) == N) R.set_i(kRFirstCov, ts.step[lane]);
+                    if (flags & kFlagJain) shaped += fdiv(p.jain_bonus * (ts.jain[lane] - Real(0.5)), (Real)N);
+                }
+                // commit the record (uav_env.py:487 and the counters of :300-307)
+                const float x = ts.x[lane], y = ts.y[lane];
+                const double battery = ts.battery[lane];
+                R.set_f(kRX, x);
+                R.set_f(kRY, y);
+                R.set_d(kRBattery, battery);
+                R.set_f(kRElapsed, ts.elapsed[lane]);
+                R.set_i(kRStep, ts.step[lane]);
+                R.set_d(kRTotalReward, R.d(kRTotalReward) + (double)reward);
+                R.set_d(kREpReturn, R.d(kREpReturn) + (double)shaped);
+                R.set_f(kRLastBytes, (float)total_bytes);
+                if (flags & kFlagEdge) R.set_i(kREdge, R.i32(kREdge) + 1);
+                if (!collect) {
+                    if (!(flags & kFlagMoveOk)) R.set_i(kRBoundary, R.i32(kRBoundary) + 1);
+                } else {
+                    R.w(kRVisLo) = vis_lo;
+                    R.w(kRVisHi) = vis_hi;
+                    R.set_d(kRTotalData, R.d(kRTotalData) + (double)total_bytes);
+                    R.set_i(kRCapture, R.i32(kRCapture) + ((counts >> 8) & 0xf));
+                    R.set_i(kRCollisions, R.i32(kRCollisions) + (counts & 0xff));
+                    R.set_i(kRDelivered, R.i32(kRDelivered) + ((counts >> 12) & 0xf));
+                }
+                // outputs
+                restart = truncated && p.auto_reset;
+                reinterpret_cast<Real*>(b.reward)[e] = shaped;
+                b.done[e] = truncated ? 1 : 0;
+                float* o = b.obs + (size_t)e * p.obs_stride;  // uav_env.py:644
+                if constexpr (kParity) {
+                    o[0] = (float)((double)x / (double)ts.W[lane]);
+                    o[1] = (float)((double)y / (double)ts.H[lane]);
+                    o[2] = (float)(battery / p.max_battery);
+                } else {
+                    o[0] = __fdividef(x, (float)ts.W[lane]);
+                    o[1] = __fdividef(y, (float)ts.H[lane]);
+                    o[2] = (float)battery * p.inv_max_battery;
+                }
+                if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(x, y, ts.W[lane], ts.H[lane]);
+                if (b.step_detail) {
+                    double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+                    d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
+                    d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
+                    d[UAVSIM_DETAIL_TRUNCATED] = truncated;
+                    d[14] = 0.0;
+                    d[15] = 0.0;
+                }
+            }
+            restart_mask = __ballot_sync(kFull, restart);
+        }
+        __syncwarp();
+
+        // ---- SB3 VecEnv semantics: finished episodes restart inside the same call (rare) ----
+        while (restart_mask) {
+            const int k = __ffs(restart_mask) - 1;
+            restart_mask &= restart_mask - 1;
+            __syncwarp();
+            reinterpret_cast<uint32_t*>(&ws.rec)[lane] = ts.rec[k][lane ^ k];  // unswizzle into the working record
+            __syncwarp();
+            finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, base + k, lane, ws);
+            __syncwarp();
+            ts.rec[k][lane ^ k] = reinterpret_cast<const uint32_t*>(&ws.rec)[lane];
+        }
+        __syncwarp();
+
+        // ---- tile records: shared -> global ----
+#pragma unroll
+        for (int r = 0; r < kTile; ++r)
+            if (r < ntile && (ts.flags[r] & kFlagValid))
+                reinterpret_cast<uint32_t*>(b.rec + base + r)[lane] = ts.rec[r][lane ^ r];
     }
 }
 

@@ -1,5 +1,9 @@
 // Launch entry points shared between the two kernel translation units and the C-ABI layer.
 #pragma once
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "uavsim_kernels.cuh"
 
 namespace uavsim {
@@ -16,16 +20,30 @@ cudaError_t launch_reset_f32(const Params<float>& p, const Buffers& b, const uin
 // Persistent grid: one wave of blocks at full residency (SM count x occupancy), never more blocks than
 // there are groups of kWarpsPerBlock environments.
 template <typename Kernel>
-inline int persistent_grid(Kernel k, int E) {
-    static int blocks_per_wave = 0;  // one static per kernel instantiation
-    if (blocks_per_wave == 0) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, 0);
-        blocks_per_wave = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
+inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_warp = 1) {
+    // keyed by (kernel, device): different instantiations share a function-pointer TYPE, so a plain
+    // function-local static would be shared between them
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int blocks_per_wave = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find({(const void*)k, dev});
+        if (it != cache.end()) blocks_per_wave = it->second;
     }
-    const int need = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks_per_wave == 0) {
+        int sms = 0, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, dyn_smem);
+        blocks_per_wave = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
+        std::lock_guard<std::mutex> lock(mu);
+        cache[{(const void*)k, dev}] = blocks_per_wave;
+    }
+    const int per_block = kWarpsPerBlock * envs_per_warp;
+    const int need = (E + per_block - 1) / per_block;
     return need < blocks_per_wave ? need : blocks_per_wave;
 }
 
@@ -35,12 +53,13 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
     const bool two = p.P > 32;
 #define UAVSIM_LAUNCH_STEP(R, S)                                                              \
     do {                                                                                      \
+        constexpr size_t smem = step_smem_bytes<Real, S>();                                   \
         if (p.fps == 5) {                                                                     \
             auto k = step_kernel<Real, R, S, 5>;                                              \
-            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                   \
+            k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);   \
         } else {                                                                              \
             auto k = step_kernel<Real, R, S, 3>;                                              \
-            k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, actions);                   \
+            k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);   \
         }                                                                                     \
     } while (0)
     if (replay) {

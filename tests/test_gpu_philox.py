@@ -66,11 +66,11 @@ def test_exported_draws_match_independent_philox(pkg, N):
             np.testing.assert_allclose(exp[:, 4, :], d0[:, :N], rtol=1e-12, atol=1e-12)
             np.testing.assert_allclose(exp[:, 5, :], e0[:, :N], rtol=1e-12, atol=1e-12)
             if a == 4:
-                a0, b0 = box_muller(q0[2], q0[3], 4.0)
                 q1 = call(1)
+                a0, b0 = box_muller(q1[0], q1[1], 4.0)
                 np.testing.assert_allclose(exp[:, 0, :], a0[:, :N], rtol=1e-12, atol=1e-12)
                 np.testing.assert_allclose(exp[:, 1, :], b0[:, :N], rtol=1e-12, atol=1e-12)
-                np.testing.assert_allclose(exp[:, 2, :], ((q1[0].astype(np.float64) + 0.5) * 2.0 ** -32)[:, :N], rtol=1e-15)
+                np.testing.assert_allclose(exp[:, 2, :], ((q1[2].astype(np.float64) + 0.5) * 2.0 ** -32)[:, :N], rtol=1e-15)
         else:
             d1, e1 = box_muller(q0[2], q0[3], 4.0)
             np.testing.assert_allclose(exp[:, 4, :], np.concatenate([d0, d1], 1)[:, :N], rtol=1e-12, atol=1e-12)

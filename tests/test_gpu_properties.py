@@ -1,0 +1,127 @@
+"""Size-independent properties checked at BASELINE.json's full sizes (where the oracle would take hours):
+data conservation per sensor, range invariants, snapshot/restore round trip, shard invariance as a checksum
+of checksums, statistics all-reduce payload consistency."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from __graft_entry__ import import_package
+    return import_package()
+
+
+def _run(env, steps, seed, p_collect=0.3):
+    import torch
+    g = torch.Generator(device=env.device)
+    g.manual_seed(seed)
+    E = env.num_envs
+    for _ in range(steps):
+        u = torch.rand(E, device=env.device, generator=g)
+        a = torch.randint(0, 4, (E,), device=env.device, generator=g, dtype=torch.int32)
+        a = torch.where(u < p_collect, torch.full_like(a, 4), a)
+        env.step_tensors(a)
+
+
+def test_config5_one_million_envs_conservation_and_ranges(pkg):
+    """configs[4]: 1000x1000, N=50, 1,048,576 envs.  Every byte a sensor generated is in its buffer, was
+    transmitted, or was lost: generated == buffer + transmitted + lost (uav_env / iot_sensors bookkeeping)."""
+    import torch
+    E, N = 1 << 20, 50
+    env = pkg.UAVVecEnv(E, grid_size=(1000, 1000), num_sensors=N, seed=5, action_mask=False, max_battery=20.0)
+    obs = env.reset_tensors()
+    _run(env, 150, seed=1)
+    env.poll_errors()
+    st = env.state()
+    gen = env.generated()
+    lhs = st["buffer"] + st["transmitted"] + st["lost"]
+    err = ((lhs - gen).abs() / gen.clamp_min(1.0)).max().item()
+    assert err < 2e-5, err                                    # float32 state
+    assert float(st["buffer"].min()) >= 0.0 and float(st["buffer"].max()) <= 1000.0
+    sf = st["spreading_factor"]
+    assert int(sf.min()) >= 7 and int(sf.max()) <= 12 and not bool((sf == 8).any() | (sf == 10).any())
+    assert bool(torch.isfinite(obs).all()) and float(obs.min()) >= 0.0 and float(obs.max()) <= 1.0
+    rec = env.records()
+    assert (rec["battery"] > 0).all() and (rec["battery"] <= 20.0).all()
+    assert (rec["x"] >= 0).all() and (rec["x"] < 1000).all() and (rec["y"] >= 0).all() and (rec["y"] < 1000).all()
+    assert (rec["step"] >= 0).all() and (rec["step"] <= 150).all()      # 0: restarted by this very step
+    # with a 20 Wh battery every env has finished at least one episode: the all-reduce payload says so
+    sums = env.stat_sums.cpu().numpy()
+    assert sums[-1] >= 0.99 * E and sums[-1] == (rec["episode"].astype(np.int64) - 1).sum()   # episodes finished, counted two ways
+    mean_len = sums[1] / sums[-1]
+    assert 90 < mean_len < 135, mean_len                      # 19.6 Wh / (0.139..0.194 Wh per step)
+    env.close()
+
+
+def test_config3_domain_rand_65536_envs_invariants(pkg):
+    """configs[2]: 65,536 envs, grids from the curriculum list, N = 10..50 padded to 50 observation slots."""
+    import torch
+    E = 65536
+    n = np.random.default_rng(0).integers(10, 51, size=E).astype(np.int32)
+    env = pkg.UAVVecEnv(E, num_sensors=n, max_sensors=50, domain_randomisation=True, curriculum_stage=4, seed=9,
+                        max_battery=10.0)
+    obs = env.reset_tensors()
+    assert obs.shape == (E, 153)
+    _run(env, 120, seed=2)
+    env.poll_errors()
+    rec = env.records()
+    assert (rec["num_sensors"] == n).all()
+    assert set(np.unique(rec["grid_w"])) <= {100, 200, 300, 400, 500}
+    obs = env.obs
+    ghost = torch.arange(50, device=env.device)[None, :] >= torch.as_tensor(n, device=env.device)[:, None]
+    slots = obs[:, 3:].view(E, 50, 3)
+    assert float(slots[ghost].abs().max()) == 0.0            # ghost slots stay exactly zero (dqn.py:297-298)
+    st = env.state()
+    live = ~ghost
+    lhs = (st["buffer"] + st["transmitted"] + st["lost"])[live]
+    gen = env.generated()[live]
+    assert ((lhs - gen).abs() / gen.clamp_min(1.0)).max().item() < 2e-5
+    stats = env.episode_stats.cpu().numpy()
+    fin = stats[:, 1] > 0
+    assert fin.mean() > 0.99
+    assert ((stats[fin, 6] >= 0) & (stats[fin, 6] <= 100)).all()                 # NDR %
+    assert ((stats[fin, 8] > 0) & (stats[fin, 8] <= 1.0 + 1e-9)).all()           # Jain's index
+    env.close()
+
+
+def test_snapshot_restore_round_trip(pkg):
+    import torch
+    env = pkg.UAVVecEnv(4096, grid_size=(300, 300), num_sensors=30, seed=3, max_battery=8.0)
+    env.reset_tensors()
+    _run(env, 20, seed=3)
+    snap = env.snapshot()
+    _run(env, 25, seed=4)
+    a = (env.obs.clone(), env.reward.clone(), env.done.clone(), env.snapshot())
+    env.restore(snap)
+    _run(env, 25, seed=4)
+    b = (env.obs, env.reward, env.done, env.snapshot())
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    env.close()
+
+
+def test_shard_invariance_checksum_of_checksums(pkg):
+    """The whole job's per-step reward checksum equals the sum of its shards' checksums, bit for bit."""
+    import torch
+    E, T = 65536, 40
+    acts = torch.randint(0, 5, (T, E), dtype=torch.int32, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(7))
+
+    def checksums(count, offset):
+        env = pkg.UAVVecEnv(count, grid_size=(500, 500), num_sensors=20, seed=77, env_id_offset=offset, max_battery=6.0)
+        env.reset_tensors()
+        out = []
+        for t in range(T):
+            o, r, d = env.step_tensors(acts[t, offset:offset + count])
+            out.append((r.double().sum().item(), int(d.sum().item()), o.double().sum().item()))
+        env.close()
+        return np.array(out)
+    whole = checksums(E, 0)
+    parts = [checksums(E // 4, k * (E // 4)) for k in range(4)]
+    assert (whole[:, 1] == sum(p[:, 1] for p in parts)).all()
+    np.testing.assert_allclose(whole[:, 0], sum(p[:, 0] for p in parts), rtol=1e-12)
+    np.testing.assert_allclose(whole[:, 2], sum(p[:, 2] for p in parts), rtol=1e-12)

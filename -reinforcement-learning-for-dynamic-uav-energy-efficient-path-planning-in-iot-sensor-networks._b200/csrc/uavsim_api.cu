@@ -58,7 +58,7 @@ int validate(const uavsim_config* c) {
         return fail(UAVSIM_ERR_INVALID_ARG, "obs_slots must be in [max_sensors, %d]", UAVSIM_MAX_SENSORS);
     if (c->features_per_sensor != 3 && c->features_per_sensor != 5)
         return fail(UAVSIM_ERR_INVALID_ARG, "features_per_sensor must be 3 or 5 (uav_env.py:349)");
-    if (c->frame_stack != 1) return fail(UAVSIM_ERR_UNSUPPORTED, "frame_stack > 1 is not built yet");
+    if (c->frame_stack < 1 || c->frame_stack > 16) return fail(UAVSIM_ERR_INVALID_ARG, "frame_stack must be in [1, 16]");
     if (c->precision != UAVSIM_F64 && c->precision != UAVSIM_F32)
         return fail(UAVSIM_ERR_INVALID_ARG, "precision must be UAVSIM_F64 or UAVSIM_F32");
     if (c->rng_mode != UAVSIM_RNG_REPLAY && c->rng_mode != UAVSIM_RNG_PHILOX)
@@ -165,7 +165,9 @@ Params<Real> make_params(const uavsim_config& c) {
     p.init_sf = c.init_sf;
     p.fps = c.features_per_sensor;
     p.obs_dim = 3 + c.features_per_sensor * c.obs_slots;
-    p.obs_stride = p.obs_dim;
+    p.frame_k = c.frame_stack;
+    p.frame_mirror = c.frame_stack > 1 ? c.frame_stack * p.obs_dim : 0;
+    p.obs_stride = p.obs_dim * (c.frame_stack > 1 ? 2 * c.frame_stack : 1);
     p.P = c.max_sensors;
     p.domain_rand = c.reset_mode == UAVSIM_RESET_DOMAIN_RAND;
     p.auto_reset = c.auto_reset != 0;
@@ -236,6 +238,7 @@ struct uavsim_handle {
     Params<float> p32;
     Buffers buf;
     bool outputs_bound = false;
+    int frame_slot = -1;  // row the newest frame was written to; -1 before the first reset
     int64_t launches = 0;
     int32_t* actions_dev = nullptr;
 };
@@ -313,7 +316,7 @@ int uavsim_query_dims(const uavsim_config* c, uavsim_dims* out) {
     if (!out) return fail(UAVSIM_ERR_INVALID_ARG, "out is NULL");
     std::memset(out, 0, sizeof *out);
     out->obs_dim = 3 + c->features_per_sensor * c->obs_slots;
-    out->frame_rows = 1;
+    out->frame_rows = c->frame_stack > 1 ? 2 * c->frame_stack : 1;
     out->obs_row_floats = out->obs_dim * out->frame_rows;
     out->real_bytes = real_bytes(c);
     out->arena_bytes = make_layout(c).total;
@@ -556,6 +559,9 @@ static int check_ready(uavsim_handle* h, bool reset) {
 int uavsim_reset(uavsim_handle* h, const uint8_t* mask, void* stream) {
     if (int rc = check_ready(h, true)) return rc;
     const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    const int k = h->cfg.frame_stack;
+    if (!mask || h->frame_slot < 0) h->frame_slot = k - 1;  // a full reset restarts the ring: window = k-1 zero frames + obs
+    h->buf.frame_slot = h->frame_slot;
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_reset_f64(h->p64, h->buf, mask, replay, (cudaStream_t)stream)
                                                    : launch_reset_f32(h->p32, h->buf, mask, replay, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "reset_kernel launch");
@@ -567,7 +573,10 @@ int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
     if (int rc = check_ready(h, false)) return rc;
     if (!actions) return fail(UAVSIM_ERR_INVALID_ARG, "actions is NULL");
     const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
     h->buf.step_serial += 1;
+    h->frame_slot = (h->frame_slot + 1) % h->cfg.frame_stack;
+    h->buf.frame_slot = h->frame_slot;
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_step_f64(h->p64, h->buf, actions, replay, (cudaStream_t)stream)
                                                    : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "step_kernel launch");
@@ -583,8 +592,15 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
     const size_t E = (size_t)h->cfg.num_envs;
     CUDA_TRY(cudaMemcpyAsync(h->actions_dev, actions_host, E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (int rc = uavsim_step(h, h->actions_dev, stream)) return rc;
-    if (obs_host)
-        CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs, E * h->dims.obs_row_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (obs_host) {  // the stacked window [E][k*obs_dim] (a strided slice of the mirrored ring when k > 1)
+        const size_t k = (size_t)h->cfg.frame_stack, od = (size_t)h->dims.obs_dim;
+        if (k == 1)
+            CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs, E * od * sizeof(float), cudaMemcpyDeviceToHost, st));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(obs_host, k * od * sizeof(float), h->buf.obs + (size_t)(h->frame_slot + 1) * od,
+                                       (size_t)h->dims.obs_row_floats * sizeof(float), k * od * sizeof(float), E,
+                                       cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(reward_host, h->buf.reward, E * h->dims.real_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(done_host, h->buf.done, E, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -611,5 +627,7 @@ int uavsim_stat_sums(uavsim_handle* h, double** sums) {
 }
 
 int64_t uavsim_launch_count(const uavsim_handle* h) { return h ? h->launches : 0; }
+
+int uavsim_frame_slot(const uavsim_handle* h) { return h ? h->frame_slot : -1; }
 
 }  // extern "C"

@@ -73,6 +73,7 @@ struct Params {
     float inv_max_battery, inv_maxbuf, inv_rate;
     double min_start_dist;
     int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
+    int32_t frame_k, frame_mirror;  // VecFrameStack: k frames; offset (floats) of the mirrored copy, 0 when k == 1
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     uint32_t key0, key1;
     int64_t env_id_offset;
@@ -108,7 +109,17 @@ struct Buffers {
     unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
     int32_t E;
     uint32_t step_serial;
+    int32_t frame_slot;  // row of the (2k-row mirrored ring) frame block this launch writes
 };
+
+// Frame stacking (VecFrameStack, dqn.py:1278; extractor layout dqn.py:612-620) without a shift pass: each
+// environment owns 2k frame rows; the frame of a step is written to rows s and s+k (s = step mod k), so the
+// k most recent frames, oldest first, are always the CONTIGUOUS rows s+1 .. s+k -- the host exposes that
+// window as a strided zero-copy view.  With k == 1 there is one row and no mirror.
+template <typename Real>
+__device__ __forceinline__ float* obs_frame(const Params<Real>& p, const Buffers& b, int e) {
+    return b.obs + (size_t)e * p.obs_stride + b.frame_slot * p.obs_dim;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -614,10 +625,11 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 // into the row (the partial sectors of neighbouring lanes merge in L2; DRAM sees the row once); ghost
 // slots are zero-filled when the buffer is bound / an episode starts and never touched by a step (N is
 // fixed during an episode).
-template <typename Real, bool REPLAY, int SPL, int FPS, bool HEAD>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool HEAD, bool MIRROR>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
                                         const Draws<Real, REPLAY, SPL>& dr, int lane, float* __restrict__ out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
+    const int mirror = MIRROR ? p.frame_mirror : 0;
     Real dd[SPL], de[SPL];
     dr.obs(p, lane, dd, de);
     float inv_w = 0.f, inv_h = 0.f;
@@ -644,17 +656,23 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
         const bool in_range = (s[k].det + de[k]) >= p.thr;
         if (s[k].active) {
             float* o = out + 3 + FPS * j;
-            o[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
-            o[1] = (float)urg;
-            o[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
+            float f[FPS];
+            f[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
+            f[1] = (float)urg;
+            f[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
             if constexpr (FPS == 5) {  // include_sensor_positions, uav_env.py:668-672
                 if constexpr (kParity) {
-                    o[3] = (float)(((double)s[k].sx - (double)h.x) / (double)h.W);
-                    o[4] = (float)(((double)s[k].sy - (double)h.y) / (double)h.H);
+                    f[3] = (float)(((double)s[k].sx - (double)h.x) / (double)h.W);
+                    f[4] = (float)(((double)s[k].sy - (double)h.y) / (double)h.H);
                 } else {
-                    o[3] = (s[k].sx - h.x) * inv_w;
-                    o[4] = (s[k].sy - h.y) * inv_h;
+                    f[3] = (s[k].sx - h.x) * inv_w;
+                    f[4] = (s[k].sy - h.y) * inv_h;
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < FPS; ++q) {
+                o[q] = f[q];
+                if constexpr (MIRROR) o[q + mirror] = f[q];
             }
         }
     }
@@ -918,9 +936,18 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     dr.step = 0;
     dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = exp;
-    float* out = b.obs + (size_t)e * p.obs_stride;
-    observe<Real, REPLAY, SPL, FPS, true>(p, h, s, dr, lane, out);
+    float* out = obs_frame(p, b, e);
+    if (p.frame_k > 1) {  // a new episode starts with k-1 all-zero frames (VecFrameStack zeroes the stack on done)
+        float* blk = b.obs + (size_t)e * p.obs_stride;
+        for (int i = lane; i < p.obs_stride; i += 32) blk[i] = 0.0f;
+        __syncwarp();
+    }
+    observe<Real, REPLAY, SPL, FPS, true, false>(p, h, s, dr, lane, out);
     for (int i = 3 + FPS * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
+    if (p.frame_k > 1) {
+        __syncwarp();
+        for (int i = lane; i < p.obs_dim; i += 32) out[i + p.frame_mirror] = out[i];
+    }
     const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
     __syncwarp();
     if (lane == 0) {
@@ -1295,11 +1322,11 @@ template <typename Real, bool REPLAY, int SPL, int FPS>
 __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buffers& b, int e, int lane, WarpSmem& ws) {
     __syncwarp();
     const int N = ws.rec.num_sensors;
-    if (b.terminal_obs) {
-        const int n = 3 + FPS * N;
-        float* t = b.terminal_obs + (size_t)e * p.obs_dim;
-        const float* row = b.obs + (size_t)e * p.obs_stride;  // written by this warp a moment ago
-        for (int i = lane; i < p.obs_dim; i += 32) t[i] = i < n ? row[i] : 0.0f;
+    if (b.terminal_obs) {  // the k stacked frames ending with the terminal one (written by this warp a moment ago)
+        const int total = p.frame_k * p.obs_dim;
+        float* t = b.terminal_obs + (size_t)e * total;
+        const float* win = b.obs + (size_t)e * p.obs_stride + (p.frame_k > 1 ? (b.frame_slot + 1) * p.obs_dim : 0);
+        for (int i = lane; i < total; i += 32) t[i] = win[i];
     }
     Sensor<Real> s[SPL];
     load_sensors<Real, SPL>(b, p, e, N, lane, s);
@@ -1384,7 +1411,7 @@ struct RecView {  // lane-private access to record l of the swizzled tile
 };
 
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.
-template <typename Real, bool REPLAY, int SPL, int FPS>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
 __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
                                              int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
     constexpr bool kParity = std::is_same<Real, double>::value;
@@ -1456,7 +1483,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     }
 
     // ---- observation, sensor part (uav_env.py:638-674); obs[0..2] are written by phase C ----
-    observe<Real, REPLAY, SPL, FPS, false>(p, h, s, dr, lane, b.obs + (size_t)e * p.obs_stride);
+    observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, dr, lane, obs_frame(p, b, e));
 
     // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
     float cur_dist = 0.f;
@@ -1516,7 +1543,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
-template <typename Real, bool REPLAY, int SPL, int FPS>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
@@ -1649,7 +1676,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
                 if (!(ts.flags[k] & kFlagValid)) continue;
                 load_sensors<Real, SPL>(b, p, e, ts.N[k], lane, s);
             }
-            sensor_phase<Real, REPLAY, SPL, FPS>(p, b, ts, ws, k, e, lane, s);
+            sensor_phase<Real, REPLAY, SPL, FPS, STACK>(p, b, ts, ws, k, e, lane, s);
         }
         __syncwarp();
 
@@ -1725,15 +1752,24 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
                 restart = truncated && p.auto_reset;
                 reinterpret_cast<Real*>(b.reward)[e] = shaped;
                 b.done[e] = truncated ? 1 : 0;
-                float* o = b.obs + (size_t)e * p.obs_stride;  // uav_env.py:644
+                float* o = obs_frame(p, b, e);  // uav_env.py:644
+                float f0, f1, f2;
                 if constexpr (kParity) {
-                    o[0] = (float)((double)x / (double)ts.W[lane]);
-                    o[1] = (float)((double)y / (double)ts.H[lane]);
-                    o[2] = (float)(battery / p.max_battery);
+                    f0 = (float)((double)x / (double)ts.W[lane]);
+                    f1 = (float)((double)y / (double)ts.H[lane]);
+                    f2 = (float)(battery / p.max_battery);
                 } else {
-                    o[0] = __fdividef(x, (float)ts.W[lane]);
-                    o[1] = __fdividef(y, (float)ts.H[lane]);
-                    o[2] = (float)battery * p.inv_max_battery;
+                    f0 = __fdividef(x, (float)ts.W[lane]);
+                    f1 = __fdividef(y, (float)ts.H[lane]);
+                    f2 = (float)battery * p.inv_max_battery;
+                }
+                o[0] = f0;
+                o[1] = f1;
+                o[2] = f2;
+                if constexpr (STACK) {
+                    o[p.frame_mirror] = f0;
+                    o[p.frame_mirror + 1] = f1;
+                    o[p.frame_mirror + 2] = f2;
                 }
                 if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(x, y, ts.W[lane], ts.H[lane]);
                 if (b.step_detail) {

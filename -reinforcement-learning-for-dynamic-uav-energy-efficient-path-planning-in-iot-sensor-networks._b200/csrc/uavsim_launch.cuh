@@ -54,13 +54,10 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
 #define UAVSIM_LAUNCH_STEP(R, S)                                                              \
     do {                                                                                      \
         constexpr size_t smem = step_smem_bytes<Real, S>();                                   \
-        if (p.fps == 5) {                                                                     \
-            auto k = step_kernel<Real, R, S, 5>;                                              \
-            k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);   \
-        } else {                                                                              \
-            auto k = step_kernel<Real, R, S, 3>;                                              \
-            k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);   \
-        }                                                                                     \
+        const bool stack = p.frame_k > 1;                                                     \
+        auto k = p.fps == 5 ? (stack ? step_kernel<Real, R, S, 5, true> : step_kernel<Real, R, S, 5, false>)  \
+                            : (stack ? step_kernel<Real, R, S, 3, true> : step_kernel<Real, R, S, 3, false>); \
+        k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);       \
     } while (0)
     if (replay) {
         if (two)

@@ -69,7 +69,7 @@ class UAVVecEnv:
                  penalty_data_loss=-1.0, reward_urgency_reduction=20.0, penalty_battery=-0.5,
                  reward_movement=10.0, include_sensor_positions=False,
                  # batched-simulator arguments
-                 max_sensors: Optional[int] = None, obs_slots: Optional[int] = None,
+                 max_sensors: Optional[int] = None, obs_slots: Optional[int] = None, n_stack: int = 1,
                  domain_randomisation=False, curriculum_stage=0,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
                  device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
@@ -89,6 +89,7 @@ class UAVVecEnv:
         cfg.obs_slots = int(obs_slots if obs_slots is not None else
                             (MAX_SENSORS_LIMIT if domain_randomisation and P <= MAX_SENSORS_LIMIT else P))
         cfg.features_per_sensor = 5 if include_sensor_positions else 3
+        cfg.frame_stack = int(n_stack)          # VecFrameStack(n_stack) on device (dqn.py:1098,1278)
         cfg.precision = {"f64": N.F64, "f32": N.F32}[precision]
         cfg.rng_mode = {"replay": N.RNG_REPLAY, "philox": N.RNG_PHILOX}[rng]
         cfg.reset_mode = N.RESET_DOMAIN_RAND if domain_randomisation else N.RESET_FIXED
@@ -135,17 +136,20 @@ class UAVVecEnv:
             N.check(self.lib.uavsim_create(C.byref(cfg), _ptr(self._arena), self._arena.numel(),
                                            self._stream(), C.byref(h)))
             self._h = h
-            self.obs = torch.empty((E, self.dims.obs_dim), dtype=torch.float32, device=dev)
+            self.n_stack = int(n_stack)
+            self.stacked_dim = self.n_stack * self.dims.obs_dim
+            # frame block per env: one row, or the 2k-row mirrored ring (include/uavsim.h, uavsim_outputs.obs)
+            self._obs_buf = torch.empty((E, self.dims.obs_row_floats), dtype=torch.float32, device=dev)
             self.reward = torch.empty((E,), dtype=self.real_dtype, device=dev)
             self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
-            self.terminal_obs = torch.zeros((E, self.dims.obs_dim), dtype=torch.float32, device=dev)
+            self.terminal_obs = torch.zeros((E, self.stacked_dim), dtype=torch.float32, device=dev)
             self.episode_stats = torch.zeros((E, N.STAT_COUNT), dtype=torch.float64, device=dev)
             self.action_mask = torch.zeros((E,), dtype=torch.uint8, device=dev) if action_mask else None
             self.step_detail = (torch.zeros((E, N.DETAIL_COUNT), dtype=torch.float64, device=dev)
                                 if step_detail else None)
             self.draw_export = (torch.full((E, N.NUM_SLOTS, P), float("nan"), dtype=self.real_dtype, device=dev)
                                 if export_draws else None)
-            out = N.Outputs(_ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.terminal_obs),
+            out = N.Outputs(_ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done), _ptr(self.terminal_obs),
                             _ptr(self.episode_stats), _ptr(self.action_mask), _ptr(self.step_detail),
                             _ptr(self.draw_export))
             N.check(self.lib.uavsim_bind_outputs(self._h, C.byref(out), self._stream()))
@@ -177,13 +181,25 @@ class UAVVecEnv:
         self.last_episode_stats = [None] * E
         self.observation_space = Box(low=-np.inf if domain_randomisation else -1.0,
                                      high=np.inf if domain_randomisation else 1.0,
-                                     shape=(self.dims.obs_dim,), dtype=np.float32)
+                                     shape=(self.stacked_dim,), dtype=np.float32)
         self.action_space = Discrete(N.NUM_ACTIONS)
         self.render_mode = None
         self.metadata = {"render_modes": []}
         self._closed = False
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def obs(self) -> torch.Tensor:
+        """The current (stacked) observation [E, n_stack*obs_dim] as a zero-copy view of the bound buffer.
+        With n_stack > 1 it is the window of the k newest frames, oldest first (VecFrameStack order), of the
+        mirrored frame ring; the view moves every step, so fetch it again after each step."""
+        if self.n_stack == 1:
+            return self._obs_buf
+        s = int(self.lib.uavsim_frame_slot(self._h))
+        od = self.dims.obs_dim
+        return self._obs_buf.as_strided((self.num_envs, self.stacked_dim), (self.dims.obs_row_floats, 1),
+                                        storage_offset=(max(s, 0) + 1) * od)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -280,7 +296,7 @@ class UAVVecEnv:
         """Pinned host buffers for `step_host` (actions in; obs, reward, done out)."""
         E = self.num_envs
         return dict(actions=torch.zeros((E,), dtype=torch.int32).pin_memory(),
-                    obs=torch.empty((E, self.dims.obs_dim), dtype=torch.float32).pin_memory(),
+                    obs=torch.empty((E, self.stacked_dim), dtype=torch.float32).pin_memory(),
                     reward=torch.empty((E,), dtype=self.real_dtype).pin_memory(),
                     done=torch.empty((E,), dtype=torch.uint8).pin_memory())
 

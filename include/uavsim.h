@@ -78,7 +78,8 @@ typedef struct uavsim_config {
     int32_t max_sensors;  /* P, sensor slots per env row (>= every env's N, <= UAVSIM_MAX_SENSORS) */
     int32_t obs_slots;    /* sensor slots in the observation row (zero padded; 50 for the attention extractor, dqn.py:121,567-571) */
     int32_t features_per_sensor; /* 3, or 5 with include_sensor_positions (uav_env.py:349,668-672) */
-    int32_t frame_stack;  /* k frames kept per env, newest last (VecFrameStack, dqn.py:1278); 1 = none */
+    int32_t frame_stack;  /* k frames kept per env, newest last (VecFrameStack, dqn.py:1278; k=4 training, k=10 extractor
+                             layout dqn.py:570,612-620); 1 = none.  See uavsim_dims.frame_rows. */
     int32_t precision;    /* uavsim_precision */
     int32_t rng_mode;     /* uavsim_rng_mode */
     int32_t reset_mode;   /* uavsim_reset_mode */
@@ -188,10 +189,13 @@ enum {
 /* Output buffers, allocated by the caller (e.g. torch tensors -> zero-copy), borrowed by the library.
  * reward dtype follows precision (float64 / float32).  Nullable members are optional. */
 typedef struct uavsim_outputs {
-    float* obs;            /* [E][frame_stack_rows][obs_dim]; see uavsim_query_dims */
+    float* obs;            /* [E][frame_rows][obs_dim].  frame_stack == 1: one row.  frame_stack == k > 1: a mirrored ring
+                              of 2k rows; the step's frame goes to rows s and s+k (s = uavsim_frame_slot), so the k most
+                              recent frames, oldest first, are the contiguous rows s+1..s+k: the stacked observation of
+                              env e is the k*obs_dim floats at obs + e*frame_rows*obs_dim + (s+1)*obs_dim. */
     void* reward;          /* [E] real */
     uint8_t* done;         /* [E] terminated|truncated (terminated is always false in the reference, uav_env.py:471) */
-    float* terminal_obs;   /* [E][obs_dim] last observation of a finished episode (auto_reset), nullable */
+    float* terminal_obs;   /* [E][frame_stack*obs_dim] last (stacked) observation of a finished episode (auto_reset), nullable */
     double* episode_stats; /* [E][UAVSIM_STAT_COUNT] written when an env finishes, nullable */
     uint8_t* action_mask;  /* [E] bit a set = action a valid (derived: uav.py:175; COLLECT always), nullable */
     double* step_detail;   /* [E][UAVSIM_DETAIL_COUNT] per-step diagnostics for parity tests, nullable */
@@ -209,7 +213,7 @@ enum {
 typedef struct uavsim_dims {
     int32_t obs_dim;        /* 3 + features_per_sensor*obs_slots */
     int32_t obs_row_floats; /* floats per env in outputs.obs (= frame rows * obs_dim) */
-    int32_t frame_rows;     /* physical frame rows per env (2k-1 mirrored ring when frame_stack>1, else 1) */
+    int32_t frame_rows;     /* physical frame rows per env: 2k (mirrored ring) when frame_stack = k > 1, else 1 */
     int32_t real_bytes;     /* 8 or 4 */
     int64_t arena_bytes;    /* device bytes uavsim_create needs for all state */
     int64_t replay_step_doubles;  /* doubles per env in a replay draw table: 6*P */
@@ -290,6 +294,9 @@ int uavsim_poll_error(uavsim_handle* h, void* stream, int64_t* first_env);
 int uavsim_stat_sums(uavsim_handle* h, double** sums_dev);
 /* Kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t uavsim_launch_count(const uavsim_handle* h);
+/* Row s of the mirrored frame ring the newest frame was written to (0 when frame_stack == 1; -1 before the
+ * first reset).  The stacked observation window starts at row s+1 (see uavsim_outputs.obs). */
+int uavsim_frame_slot(const uavsim_handle* h);
 
 #ifdef __cplusplus
 }

@@ -1025,26 +1025,31 @@ __device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& i
     imax = idx;
 }
 
-// What a COLLECT step hands back to the common tail of the step.
 template <typename Real>
-struct CollectOut {
-    Real reward, total_bytes, urg_red, mean_urg;
-    int collisions, captures, delivered;
-    bool any_new, was_empty, all_collected;
-    unsigned long long att_mask, win_mask;
-};
+struct TileSmem;
 
-// UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment.
+// Draws of the step in flight for slot k of the tile, rebuilt at each point of use (cheap) so that nothing
+// of it stays live across the step.
 template <typename Real, bool REPLAY, int SPL>
-__device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Sensor<Real> (&s)[SPL],
-                                               const Draws<Real, REPLAY, SPL>& dr, Real step_loss, int lane,
-                                               WarpSmem& ws, CollectOut<Real>& out) {
+__device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
+                                                                const TileSmem<Real>& ts, int k, int e);
+
+// UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment (slot k of the tile).
+// Results go to the tile block (and the parity diagnostics) from lane 0.
+template <typename Real, bool REPLAY, int SPL>
+__device__ __forceinline__ void collect_action(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
+                                               int k, int e, Sensor<Real> (&s)[SPL], Real step_loss, int lane) {
+    const Draws<Real, REPLAY, SPL> dr = step_draws<Real, REPLAY, SPL>(p, b, ts, k, e);
+    Hot h;
+    h.N = ts.N[k];
+    h.elapsed = ts.elapsed[k];
+    h.vis_lo = ts.vis_lo[k];
+    h.vis_hi = ts.vis_hi[k];
     constexpr bool kParity = std::is_same<Real, double>::value;
     const int N = h.N;
     float before[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) before[k] = (float)div_const(s[k].buf, p.rate, p.inv_rate);  // _get_sensor_urgencies, :386-394
-    h.battery -= p.e_hover;                                                    // uav.py:205
     const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
     // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
     Real da[SPL], db[SPL], du[SPL];
@@ -1220,18 +1225,27 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, Hot& h, Se
         }
     }
     if (all_collected) reward += p.r_completion;
-    out.reward = reward;
-    out.total_bytes = total_bytes;
-    out.urg_red = urg_red;
-    out.mean_urg = mean_urg;
-    out.collisions = collisions;
-    out.captures = captures;
-    out.delivered = delivered;
-    out.any_new = any_new;
-    out.was_empty = was_empty;
-    out.all_collected = all_collected;
-    out.att_mask = att_mask;
-    out.win_mask = win_mask;
+    if (lane == 0) {
+        ts.creward[k] = reward;
+        ts.bytes[k] = total_bytes;
+        ts.counts[k] = collisions | (captures << 8) | (delivered << 12);
+        ts.nvis_lo[k] = h.vis_lo;
+        ts.nvis_hi[k] = h.vis_hi;
+        if (b.step_detail) {  // parity diagnostics: the collect step's intermediates (phase C adds the rest)
+            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+            d[UAVSIM_DETAIL_COLLISIONS] = collisions;
+            d[UAVSIM_DETAIL_BYTES] = (double)total_bytes;
+            d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)urg_red;
+            d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)mean_urg;
+            d[UAVSIM_DETAIL_WAS_NEW] = any_new;
+            d[UAVSIM_DETAIL_WAS_EMPTY] = was_empty;
+            d[UAVSIM_DETAIL_ALL_COLLECTED] = all_collected;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)att_mask;
+            d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(att_mask >> 32);
+            d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)win_mask;
+            d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(win_mask >> 32);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1410,135 +1424,115 @@ struct RecView {  // lane-private access to record l of the swizzled tile
     }
 };
 
-// Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
-__device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
-                                             int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
-    constexpr bool kParity = std::is_same<Real, double>::value;
-    Hot h;
-    h.x = ts.x[k];
-    h.y = ts.y[k];
-    h.elapsed = ts.elapsed[k];
-    h.battery = 0.0;
-    h.W = ts.W[k];
-    h.H = ts.H[k];
-    h.N = ts.N[k];
-    h.step = ts.step[k];
-    h.vis_lo = ts.vis_lo[k];
-    h.vis_hi = ts.vis_hi[k];
-    h.episode = ts.episode[k];
-    h.prev_dist = 0.f;
-    const int flags = ts.flags[k];
-    const bool collect = flags & kFlagCollect;
-    const int N = h.N;
-    const Real dt = collect ? p.cd : Real(1);
-
+template <typename Real, bool REPLAY, int SPL>
+__device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
+                                                                const TileSmem<Real>& ts, int k, int e) {
     const uint64_t gid = (uint64_t)(p.env_id_offset + e);
     Draws<Real, REPLAY, SPL> dr;
     dr.env_lo = (uint32_t)gid;
     dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
-    dr.episode = h.episode - 1;  // the record counts resets done; the running episode is one less
-    dr.step = (uint32_t)h.step;
+    dr.episode = ts.episode[k] - 1;  // the record counts resets done; the running episode is one less
+    dr.step = (uint32_t)ts.step[k];
     dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-    dr.exp = nullptr;
+    dr.exp = (!REPLAY && b.draw_export) ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
+                                        : nullptr;
+    return dr;
+}
+
+// Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
+// the environment are read from the tile block where they are used and results are written back as soon as
+// they exist, so that little besides the sensor registers is live across the phase.
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
+__device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
+                                             int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    const int flags = ts.flags[k];
+    const bool collect = flags & kFlagCollect;
+    const int N = ts.N[k];
+
     if (!REPLAY && b.draw_export) {
-        dr.exp = reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P;
+        Real* exp = reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P;
         const Real nan = Real(CUDART_NAN);
-        for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) dr.exp[i] = nan;
+        for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
         __syncwarp();
     }
 
     // ---- iot_sensors.py:114-125: age the buffers ----
-    Real loss[SPL];
-    const Real nw = p.rate * dt;
-    bool any_over = false;
-#pragma unroll
-    for (int k2 = 0; k2 < SPL; ++k2) {
-        if constexpr (kParity) s[k2].gen += nw;
-        const Real pot = s[k2].buf + nw;
-        const bool over = pot > p.maxbuf;
-        loss[k2] = over ? pot - p.maxbuf : Real(0);
-        s[k2].buf = over ? p.maxbuf : pot;
-        s[k2].lost += loss[k2];  // + 0 when not saturated: no effect on the stored value
-        any_over |= (s[k2].active && over);
-    }
     Real step_loss = Real(0);
-    if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
-
-    compute_det(p, h.x, h.y, s);  // the UAV has already moved (phase A)
-    CollectOut<Real> co;
-    co.reward = co.total_bytes = co.urg_red = co.mean_urg = Real(0);
-    co.collisions = co.captures = co.delivered = 0;
-    co.any_new = co.was_empty = co.all_collected = false;
-    co.att_mask = co.win_mask = 0ull;
-    if (collect) collect_action<Real, REPLAY, SPL>(p, h, s, dr, step_loss, lane, ws, co);
-
-    int starved = 0;  // reward_function.py:59-67 (counted only when the episode ends this step)
-    if (flags & kFlagTruncated) {
+    {
+        Real loss[SPL];
+        const Real nw = p.rate * (collect ? p.cd : Real(1));
+        bool any_over = false;
 #pragma unroll
         for (int k2 = 0; k2 < SPL; ++k2) {
-            const Real g = generated_of(p, s[k2], h.elapsed);
+            if constexpr (kParity) s[k2].gen += nw;
+            const Real pot = s[k2].buf + nw;
+            const bool over = pot > p.maxbuf;
+            loss[k2] = over ? pot - p.maxbuf : Real(0);
+            s[k2].buf = over ? p.maxbuf : pot;
+            s[k2].lost += loss[k2];  // + 0 when not saturated: no effect on the stored value
+            any_over |= (s[k2].active && over);
+        }
+        if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
+        if (lane == 0) ts.step_loss[k] = step_loss;
+    }
+
+    compute_det(p, ts.x[k], ts.y[k], s);  // the UAV has already moved (phase A)
+    if (collect) collect_action<Real, REPLAY, SPL>(p, b, ts, ws, k, e, s, step_loss, lane);
+
+    if (flags & kFlagTruncated) {  // reward_function.py:59-67 (counted only when the episode ends this step)
+        int starved = 0;
+        const float elapsed = ts.elapsed[k];
+#pragma unroll
+        for (int k2 = 0; k2 < SPL; ++k2) {
+            const Real g = generated_of(p, s[k2], elapsed);
             starved += __popc(__ballot_sync(kFull, s[k2].active && g > Real(0) && fdiv(s[k2].tx, g) < p.cr_thr));
         }
+        if (lane == 0) ts.counts[k] |= starved << 16;
     }
 
     // ---- observation, sensor part (uav_env.py:638-674); obs[0..2] are written by phase C ----
-    observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, dr, lane, obs_frame(p, b, e));
+    {
+        Hot h;
+        h.x = ts.x[k];
+        h.y = ts.y[k];
+        h.elapsed = ts.elapsed[k];
+        h.W = ts.W[k];
+        h.H = ts.H[k];
+        h.N = N;
+        h.battery = 0.0;
+        observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL>(p, b, ts, k, e), lane,
+                                                       obs_frame(p, b, e));
+    }
 
     // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
-    float cur_dist = 0.f;
-    Real jain = Real(0);
-    bool have_jain = false;
     if (p.domain_rand) {
-        cur_dist = nearest_with_data(h.x, h.y, s);
+        const float cur_dist = nearest_with_data(ts.x[k], ts.y[k], s);
+        const float elapsed = ts.elapsed[k];
         Real r1[SPL], r2[SPL];
         int cnt = 0;
 #pragma unroll
         for (int k2 = 0; k2 < SPL; ++k2) {
-            const Real g = generated_of(p, s[k2], h.elapsed);
+            const Real g = generated_of(p, s[k2], elapsed);
             const bool has = s[k2].active && g > Real(0);
             const Real rate = has ? fdiv(s[k2].tx, g) * Real(100) : Real(0);
             r1[k2] = rate;
             r2[k2] = rate * rate;
             cnt += __popc(__ballot_sync(kFull, has));
         }
+        Real jain = Real(0);
         if (cnt > 0) {
             const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
             const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
             jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
-            have_jain = true;
+        }
+        if (lane == 0) {
+            ts.cur_dist[k] = cur_dist;
+            ts.jain[k] = jain;
+            if (cnt > 0) ts.flags[k] = flags | kFlagJain;
         }
     }
     store_sensors<Real, SPL>(b, p, e, lane, s, false);
-
-    if (lane == 0) {
-        ts.step_loss[k] = step_loss;
-        ts.cur_dist[k] = cur_dist;
-        ts.jain[k] = jain;
-        if (have_jain) ts.flags[k] = flags | kFlagJain;
-        ts.counts[k] = starved << 16;
-        if (collect) {
-            ts.creward[k] = co.reward;
-            ts.bytes[k] = co.total_bytes;
-            ts.counts[k] = co.collisions | (co.captures << 8) | (co.delivered << 12) | (starved << 16);
-            ts.nvis_lo[k] = h.vis_lo;
-            ts.nvis_hi[k] = h.vis_hi;
-        }
-        if (b.step_detail) {  // parity diagnostics: the collect step's intermediates (phase C adds the rest)
-            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
-            d[UAVSIM_DETAIL_COLLISIONS] = co.collisions;
-            d[UAVSIM_DETAIL_BYTES] = (double)co.total_bytes;
-            d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)co.urg_red;
-            d[UAVSIM_DETAIL_MEAN_URGENCY] = (double)co.mean_urg;
-            d[UAVSIM_DETAIL_WAS_NEW] = co.any_new;
-            d[UAVSIM_DETAIL_WAS_EMPTY] = co.was_empty;
-            d[UAVSIM_DETAIL_ALL_COLLECTED] = co.all_collected;
-            d[UAVSIM_DETAIL_ATTEMPT_MASK_LO] = (double)(uint32_t)co.att_mask;
-            d[UAVSIM_DETAIL_ATTEMPT_MASK_HI] = (double)(uint32_t)(co.att_mask >> 32);
-            d[UAVSIM_DETAIL_WINNER_MASK_LO] = (double)(uint32_t)co.win_mask;
-            d[UAVSIM_DETAIL_WINNER_MASK_HI] = (double)(uint32_t)(co.win_mask >> 32);
-        }
-    }
 }
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
@@ -1644,6 +1638,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
                 ts.used[lane] = used;
             }
             ts.flags[lane] = my_flags;
+            ts.counts[lane] = 0;
         }
         __syncwarp();
 
@@ -1774,6 +1769,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
                 if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(x, y, ts.W[lane], ts.H[lane]);
                 if (b.step_detail) {
                     double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+                    if (!collect)  // a collect step's intermediates were written by phase B
+                        for (int i = 0; i < UAVSIM_DETAIL_BASE_REWARD; ++i) d[i] = 0.0;
                     d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
                     d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
                     d[UAVSIM_DETAIL_TRUNCATED] = truncated;

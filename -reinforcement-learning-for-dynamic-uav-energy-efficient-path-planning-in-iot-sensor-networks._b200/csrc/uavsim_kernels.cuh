@@ -981,6 +981,18 @@ constexpr int min_blocks_per_sm() {
     return std::is_same<Real, double>::value ? 1 : 3;
 }
 
+// Block shape of the step kernel.  The one-slot-per-lane kernel fits 80 registers: 8 warps x 3 blocks per
+// SM.  The two-slot kernel needs ~100 registers to stay out of local memory (with most of the SM given to
+// shared memory the L1 is small, so a spill is an L2 round trip): 10 warps x 2 blocks per SM.
+template <typename Real, int SPL>
+__host__ __device__ constexpr int step_warps() {
+    return (!std::is_same<Real, double>::value && SPL == 2) ? 10 : 8;
+}
+template <typename Real, int SPL>
+__host__ __device__ constexpr int step_min_blocks() {
+    return std::is_same<Real, double>::value ? 1 : (SPL == 2 ? 2 : 3);
+}
+
 template <typename Real, bool REPLAY, int SPL, int FPS>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     reset_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b, const uint8_t* mask) {
@@ -1376,6 +1388,8 @@ struct alignas(16) TileSmem {
     float cur_dist[kTile];
     int32_t counts[kTile];  // collisions | captures << 8 | delivered << 12 | starved << 16
     uint32_t nvis_lo[kTile], nvis_hi[kTile];
+    int32_t n_first_next;  // sensor count of the first environment of this warp's next tile (staging)
+    int32_t pad[3];
 };
 
 // Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
@@ -1388,7 +1402,7 @@ struct alignas(16) StepWarpSmem {
 };
 template <typename Real, int SPL>
 constexpr size_t step_smem_bytes() {
-    return sizeof(StepWarpSmem<Real, SPL>) * kWarpsPerBlock;
+    return sizeof(StepWarpSmem<Real, SPL>) * step_warps<Real, SPL>();
 }
 
 enum : int {
@@ -1538,7 +1552,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
 template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
-__global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
+__global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<Real, SPL>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
     constexpr bool kParity = std::is_same<Real, double>::value;
@@ -1549,22 +1563,23 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     WarpSmem& ws = mine.ws;
     TileSmem<Real>& ts = mine.ts;
     StageBuf<Real, SPL>* stage = mine.stage;
-    const int E = b.E;
-    const int tile_stride = gridDim.x * kWarpsPerBlock * kTile;
-    int base = (blockIdx.x * kWarpsPerBlock + warp) * kTile;
-    int cur = 0;
+    // loop-invariant scalars are re-derived from the constant bank where they are used instead of being
+    // carried in registers: with 184 KB of the SM given to shared memory the L1 is small and a spilled
+    // loop-carried value costs an L2 round trip per environment
+#define UAVSIM_E (b.E)
+#define UAVSIM_TILE_STRIDE ((int)gridDim.x * step_warps<Real, SPL>() * kTile)
+    int base = (blockIdx.x * step_warps<Real, SPL>() + warp) * kTile;
     if constexpr (kStaged) {  // prime the pipeline with the first environment of the first tile
-        if (base < E)
-            stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane,
-                                   stage[0]);
+        if (base < UAVSIM_E)
+            stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
         cp_async_commit();
     }
 
-    for (; base < E; base += tile_stride) {
-        const int ntile = min(kTile, E - base);
+    for (; base < UAVSIM_E; base += UAVSIM_TILE_STRIDE) {
+        const int ntile = min(kTile, UAVSIM_E - base);
         // sensor count of the first environment of this warp's NEXT tile (needed to stage it)
-        int n_first_next = 0;
-        if (kStaged && base + tile_stride < E) n_first_next = b.rec[base + tile_stride].num_sensors;
+        if (kStaged && lane == 0)
+            ts.n_first_next = base + UAVSIM_TILE_STRIDE < UAVSIM_E ? b.rec[base + UAVSIM_TILE_STRIDE].num_sensors : 0;
 
         // ---- tile records: global -> swizzled shared memory (lane = word: coalesced 128-byte rows) ----
         __syncwarp();
@@ -1649,23 +1664,24 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
             if constexpr (kStaged) {
                 // launch the copies of the NEXT environment of this warp's sequence, then wait for the
                 // CURRENT environment's stage (issued one iteration ago)
+                // the stage buffers alternate with k: tiles hold an even number of environments (a partial
+                // tile can only be a warp's last one), so buffer k & 1 is always the one staged for slot k
                 int e1 = e + 1, n1 = 0;
                 if (k + 1 < ntile) {
                     n1 = (int)ts.rec[k + 1][kRN ^ (k + 1)];
                 } else {
-                    e1 = base + tile_stride;
-                    n1 = n_first_next;
+                    e1 = base + UAVSIM_TILE_STRIDE;
+                    n1 = ts.n_first_next;
                 }
-                if (e1 < E)
-                    stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[cur ^ 1]);
+                if (e1 < UAVSIM_E)
+                    stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[(k & 1) ^ 1]);
                 cp_async_commit();
                 cp_async_wait<1>();
                 __syncwarp();
                 const bool valid = ts.flags[k] & kFlagValid;
                 if (valid)
-                    load_sensors_staged<Real, SPL>(stage[cur], ts.N[k], lane, s);
+                    load_sensors_staged<Real, SPL>(stage[k & 1], ts.N[k], lane, s);
                 __syncwarp();
-                cur ^= 1;
                 if (!valid) continue;
             } else {
                 if (!(ts.flags[k] & kFlagValid)) continue;
@@ -1801,6 +1817,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
             if (r < ntile && (ts.flags[r] & kFlagValid))
                 reinterpret_cast<uint32_t*>(b.rec + base + r)[lane] = ts.rec[r][lane ^ r];
     }
+#undef UAVSIM_E
+#undef UAVSIM_TILE_STRIDE
 }
 
 }  // namespace uavsim

@@ -20,7 +20,7 @@ cudaError_t launch_reset_f32(const Params<float>& p, const Buffers& b, const uin
 // Persistent grid: one wave of blocks at full residency (SM count x occupancy), never more blocks than
 // there are groups of kWarpsPerBlock environments.
 template <typename Kernel>
-inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_warp = 1) {
+inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_warp = 1, int warps = kWarpsPerBlock) {
     // keyed by (kernel, device): different instantiations share a function-pointer TYPE, so a plain
     // function-local static would be shared between them
     static std::mutex mu;
@@ -37,12 +37,12 @@ inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_wa
         int sms = 0, occ = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, dyn_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 32 * warps, dyn_smem);
         blocks_per_wave = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
         std::lock_guard<std::mutex> lock(mu);
         cache[{(const void*)k, dev}] = blocks_per_wave;
     }
-    const int per_block = kWarpsPerBlock * envs_per_warp;
+    const int per_block = warps * envs_per_warp;
     const int need = (E + per_block - 1) / per_block;
     return need < blocks_per_wave ? need : blocks_per_wave;
 }
@@ -57,7 +57,8 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
         const bool stack = p.frame_k > 1;                                                     \
         auto k = p.fps == 5 ? (stack ? step_kernel<Real, R, S, 5, true> : step_kernel<Real, R, S, 5, false>)  \
                             : (stack ? step_kernel<Real, R, S, 3, true> : step_kernel<Real, R, S, 3, false>); \
-        k<<<persistent_grid(k, b.E, smem, kTile), kThreads, smem, st>>>(p, b, actions);       \
+        constexpr int warps = step_warps<Real, S>();                                          \
+        k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions); \
     } while (0)
     if (replay) {
         if (two)

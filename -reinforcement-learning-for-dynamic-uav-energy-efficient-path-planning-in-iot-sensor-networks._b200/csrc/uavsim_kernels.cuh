@@ -1376,7 +1376,8 @@ constexpr int kTile = 16;
 
 template <typename Real>
 struct alignas(16) TileSmem {
-    uint32_t rec[kTile][32];  // word w of record l lives at rec[l][w ^ l]
+    uint32_t rec[2][kTile][32];  // [buffer][l][w ^ l]: word w of record l; the other buffer receives the next tile
+    int32_t action[2][kTile];
     // phase A -> phase B (read as warp-wide broadcasts) and -> phase C
     float x[kTile], y[kTile], elapsed[kTile];
     int32_t N[kTile], W[kTile], H[kTile], step[kTile], flags[kTile];
@@ -1388,8 +1389,6 @@ struct alignas(16) TileSmem {
     float cur_dist[kTile];
     int32_t counts[kTile];  // collisions | captures << 8 | delivered << 12 | starved << 16
     uint32_t nvis_lo[kTile], nvis_hi[kTile];
-    int32_t n_first_next;  // sensor count of the first environment of this warp's next tile (staging)
-    int32_t pad[3];
 };
 
 // Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
@@ -1451,6 +1450,18 @@ __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real
     dr.exp = (!REPLAY && b.draw_export) ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
                                         : nullptr;
     return dr;
+}
+
+// Asynchronous copy of the records and actions of the tile starting at `base` into buffer `tb` of the tile block
+// (float32 layout: issued during phase B of the previous tile so that a tile never waits for its records).
+template <typename Real>
+__device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* actions, int base, int tb, int lane,
+                                           TileSmem<Real>& ts) {
+    const int n = min(kTile, b.E - base);
+#pragma unroll
+    for (int r = 0; r < kTile; ++r)
+        if (r < n) cp_async4(&ts.rec[tb][r][lane ^ r], reinterpret_cast<const uint32_t*>(b.rec + base + r) + lane);
+    if (lane < n) cp_async4(&ts.action[tb][lane], actions + base + lane);
 }
 
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
@@ -1569,31 +1580,36 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
 #define UAVSIM_E (b.E)
 #define UAVSIM_TILE_STRIDE ((int)gridDim.x * step_warps<Real, SPL>() * kTile)
     int base = (blockIdx.x * step_warps<Real, SPL>() + warp) * kTile;
-    if constexpr (kStaged) {  // prime the pipeline with the first environment of the first tile
-        if (base < UAVSIM_E)
+    int tb = 0;  // tile buffer in use
+    if constexpr (kStaged) {  // prime both pipelines: records of the first tile, sensor columns of its first env
+        if (base < UAVSIM_E) {
+            tile_issue<Real>(b, actions, base, 0, lane, ts);
             stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
+        }
         cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
     }
 
     for (; base < UAVSIM_E; base += UAVSIM_TILE_STRIDE) {
         const int ntile = min(kTile, UAVSIM_E - base);
-        // sensor count of the first environment of this warp's NEXT tile (needed to stage it)
-        if (kStaged && lane == 0)
-            ts.n_first_next = base + UAVSIM_TILE_STRIDE < UAVSIM_E ? b.rec[base + UAVSIM_TILE_STRIDE].num_sensors : 0;
-
-        // ---- tile records: global -> swizzled shared memory (lane = word: coalesced 128-byte rows) ----
-        __syncwarp();
+        uint32_t(*rec)[32] = ts.rec[tb];
+        if constexpr (!kStaged) {
+            // ---- tile records: global -> swizzled shared memory (lane = word: coalesced 128-byte rows) ----
+            __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kTile; ++r)
-            if (r < ntile) ts.rec[r][lane ^ r] = reinterpret_cast<const uint32_t*>(b.rec + base + r)[lane];
-        __syncwarp();
+            for (int r = 0; r < kTile; ++r)
+                if (r < ntile) rec[r][lane ^ r] = reinterpret_cast<const uint32_t*>(b.rec + base + r)[lane];
+            if (lane < ntile) ts.action[tb][lane] = actions[base + lane];
+            __syncwarp();
+        }
 
         // ---- phase A: one environment per lane ----
-        const RecView R{ts.rec[lane & (kTile - 1)], lane & (kTile - 1)};
+        const RecView R{rec[lane & (kTile - 1)], lane & (kTile - 1)};
         if (lane < ntile) {
             const int e = base + lane;
             int my_flags = 0;
-            const int my_action = actions[e];
+            const int my_action = ts.action[tb][lane];
             if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
                 atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
             } else {
@@ -1666,17 +1682,27 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                 // CURRENT environment's stage (issued one iteration ago)
                 // the stage buffers alternate with k: tiles hold an even number of environments (a partial
                 // tile can only be a warp's last one), so buffer k & 1 is always the one staged for slot k
+                // The NEXT tile's records + actions are requested at k == 1 (one more group in flight for two
+                // iterations) and have landed long before k reaches the end of the tile.
                 int e1 = e + 1, n1 = 0;
                 if (k + 1 < ntile) {
-                    n1 = (int)ts.rec[k + 1][kRN ^ (k + 1)];
+                    n1 = (int)rec[k + 1][kRN ^ (k + 1)];
                 } else {
                     e1 = base + UAVSIM_TILE_STRIDE;
-                    n1 = ts.n_first_next;
+                    if (e1 < UAVSIM_E) n1 = (int)ts.rec[tb ^ 1][0][kRN];
                 }
                 if (e1 < UAVSIM_E)
                     stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[(k & 1) ^ 1]);
                 cp_async_commit();
-                cp_async_wait<1>();
+                if (k == 1) {
+                    if (base + UAVSIM_TILE_STRIDE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, base + UAVSIM_TILE_STRIDE, tb ^ 1, lane, ts);
+                    cp_async_commit();
+                }
+                if (k == 1 || k == 2)
+                    cp_async_wait<2>();
+                else
+                    cp_async_wait<1>();
                 __syncwarp();
                 const bool valid = ts.flags[k] & kFlagValid;
                 if (valid)
@@ -1803,11 +1829,11 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
             const int k = __ffs(restart_mask) - 1;
             restart_mask &= restart_mask - 1;
             __syncwarp();
-            reinterpret_cast<uint32_t*>(&ws.rec)[lane] = ts.rec[k][lane ^ k];  // unswizzle into the working record
+            reinterpret_cast<uint32_t*>(&ws.rec)[lane] = rec[k][lane ^ k];  // unswizzle into the working record
             __syncwarp();
             finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, base + k, lane, ws);
             __syncwarp();
-            ts.rec[k][lane ^ k] = reinterpret_cast<const uint32_t*>(&ws.rec)[lane];
+            rec[k][lane ^ k] = reinterpret_cast<const uint32_t*>(&ws.rec)[lane];
         }
         __syncwarp();
 
@@ -1815,7 +1841,14 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
 #pragma unroll
         for (int r = 0; r < kTile; ++r)
             if (r < ntile && (ts.flags[r] & kFlagValid))
-                reinterpret_cast<uint32_t*>(b.rec + base + r)[lane] = ts.rec[r][lane ^ r];
+                reinterpret_cast<uint32_t*>(b.rec + base + r)[lane] = rec[r][lane ^ r];
+        if constexpr (kStaged) {
+            if (ntile < 4) {  // a short (= last) tile never reached the waits that retire the record group
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            tb ^= 1;
+        }
     }
 #undef UAVSIM_E
 #undef UAVSIM_TILE_STRIDE

@@ -37,6 +37,34 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// The same bijection with the ten round keys (k + r*W) supplied by the caller: the key is a per-handle
+// constant, so the schedule is computed once on the host and read from the constant bank (20 fewer integer
+// adds per call in the step kernel).
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ inline PhiloxKeys philox_key_schedule(uint32_t k0, uint32_t k1) {
+    PhiloxKeys ks;
+    for (int r = 0; r < 10; ++r) {
+        ks.k0[r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        ks.k1[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return ks;
+}
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        c0 = hi1 ^ c1 ^ ks.k0[r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ ks.k1[r];
+        c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 // stream ids (counter word 1, high byte)
 enum : uint32_t {
     kStreamStep = 0,    // per-sensor draws of a step / of the reset observation (step 0)

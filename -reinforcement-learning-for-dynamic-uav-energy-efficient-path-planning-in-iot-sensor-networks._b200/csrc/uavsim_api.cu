@@ -66,6 +66,8 @@ int validate(const uavsim_config* c) {
     if (c->reset_mode != UAVSIM_RESET_FIXED && c->reset_mode != UAVSIM_RESET_DOMAIN_RAND)
         return fail(UAVSIM_ERR_INVALID_ARG, "reset_mode must be UAVSIM_RESET_FIXED or UAVSIM_RESET_DOMAIN_RAND");
     if (c->grid_w <= 0 || c->grid_h <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "grid must be positive");
+    if ((int64_t)c->num_envs * (3 + c->features_per_sensor * c->obs_slots) * (c->frame_stack > 1 ? 2 * c->frame_stack : 1) >= (1ll << 32))
+        return fail(UAVSIM_ERR_INVALID_ARG, "num_envs * observation floats per env must be < 2^32 per handle");
     if ((int64_t)c->num_envs * c->max_sensors >= (1ll << 32))
         return fail(UAVSIM_ERR_INVALID_ARG, "num_envs * max_sensors must be < 2^32 per handle");
     if (c->max_steps <= 0 || c->max_steps >= (1 << 24))
@@ -176,6 +178,7 @@ Params<Real> make_params(const uavsim_config& c) {
     std::memcpy(p.grids, c.grids, sizeof p.grids);
     p.key0 = (uint32_t)c.seed;
     p.key1 = (uint32_t)(c.seed >> 32);
+    p.keys = philox_key_schedule(p.key0, p.key1);
     p.env_id_offset = c.env_id_offset;
     return p;
 }

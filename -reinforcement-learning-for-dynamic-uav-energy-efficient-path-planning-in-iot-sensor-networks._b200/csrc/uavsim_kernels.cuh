@@ -76,6 +76,7 @@ struct Params {
     int32_t frame_k, frame_mirror;  // VecFrameStack: k frames; offset (floats) of the mirrored copy, 0 when k == 1
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     uint32_t key0, key1;
+    PhiloxKeys keys;  // round-key schedule of (key0, key1)
     int64_t env_id_offset;
 };
 
@@ -118,7 +119,7 @@ struct Buffers {
 // window as a strided zero-copy view.  With k == 1 there is one row and no mirror.
 template <typename Real>
 __device__ __forceinline__ float* obs_frame(const Params<Real>& p, const Buffers& b, int e) {
-    return b.obs + (size_t)e * p.obs_stride + b.frame_slot * p.obs_dim;
+    return b.obs + ((uint32_t)e * (uint32_t)p.obs_stride + (uint32_t)(b.frame_slot * p.obs_dim));  // < 2^32 floats (checked at create)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,7 +330,11 @@ __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Rea
 template <typename Real>
 __device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real lost, Real gen) {
     const Real util = div_const(buf, p.maxbuf, p.inv_maxbuf);
-    const Real lr = gen > Real(0) ? fdiv(lost, gen) : Real(0);
+    Real lr;
+    if constexpr (std::is_same<Real, double>::value)
+        lr = gen > 0.0 ? lost / gen : 0.0;
+    else
+        lr = gen > 0.f ? lost * fast_rcp(gen) : 0.f;
     const Real u = util * (Real(1) + lr * Real(10));
     return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
 }
@@ -386,7 +391,7 @@ struct Draws {
 
     __device__ __forceinline__ Philox4 call(const Params<Real>& p, int lane, uint32_t c) const {
         return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c,
-                             p.key0, p.key1);
+                             p.keys);
     }
     __device__ __forceinline__ void put(const Params<Real>& p, int slot, int j, Real v) const {
         if (exp && j < p.P) exp[slot * p.P + j] = v;

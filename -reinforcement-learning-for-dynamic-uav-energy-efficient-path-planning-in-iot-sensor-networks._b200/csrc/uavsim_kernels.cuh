@@ -1064,9 +1064,15 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
     h.vis_hi = ts.vis_hi[k];
     constexpr bool kParity = std::is_same<Real, double>::value;
     const int N = h.N;
-    float before[SPL];
+    // _get_sensor_urgencies (:386-394) before the collection.  Only winners change their buffer, so the
+    // throughput build accumulates the reduction winner by winner; the parity build keeps the reference's
+    // float32 np.sum over all sensors.
+    float before[kParity ? SPL : 1];
+    float urg_red_acc = 0.f;
+    if constexpr (kParity) {
 #pragma unroll
-    for (int k = 0; k < SPL; ++k) before[k] = (float)div_const(s[k].buf, p.rate, p.inv_rate);  // _get_sensor_urgencies, :386-394
+        for (int k = 0; k < SPL; ++k) before[k] = (float)div_const(s[k].buf, p.rate, p.inv_rate);
+    }
     const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
     // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
     Real da[SPL], db[SPL], du[SPL];
@@ -1174,6 +1180,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
             }
             const int owner = winner & 31;
             got = shfl(got, owner);
+            if constexpr (!kParity) urg_red_acc += (float)got * p.inv_rate;  // (before - after) of the winner
             urg_w = shfl(urg_w, owner);
             in_range = shfl(in_range, owner);
             urg_acc += urg_w;  // np.mean over <= 6 winners adds left to right (uav_env.py:610-615)
@@ -1194,16 +1201,24 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
     }
     // Phase 5: fairness metrics (uav_env.py:596-604)
     unsigned empty_b = 0u, nonempty_b = 0u;
-    float diff[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         empty_b |= __ballot_sync(kFull, s[k].active && s[k].buf <= Real(0));
         nonempty_b |= __ballot_sync(kFull, s[k].active && !(s[k].buf <= Real(0)));
-        const float d = before[k] - (float)div_const(s[k].buf, p.rate, p.inv_rate);
-        diff[k] = d > 0.f ? d : 0.f;
     }
     const bool was_empty = empty_b != 0u, all_collected = nonempty_b == 0u;
-    const Real urg_red = (Real)sensor_sum<Real, SPL>(diff, N, lane, ws.red, kSumNumpy);  // float32 np.sum
+    Real urg_red;
+    if constexpr (kParity) {
+        float diff[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const float d = before[k] - (float)div_const(s[k].buf, p.rate, p.inv_rate);
+            diff[k] = d > 0.f ? d : 0.f;
+        }
+        urg_red = (Real)sensor_sum<Real, SPL>(diff, N, lane, ws.red, kSumNumpy);  // float32 np.sum
+    } else {
+        urg_red = urg_red_acc;
+    }
     const Real mean_urg = nwin > 0 ? fdiv(urg_acc, (Real)nwin) : Real(0);
     // Phase 6: reward_function.py:81-128, same order of additions
     Real reward = p.p_step + p.p_hover;
@@ -1223,22 +1238,34 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
             if (s[k].active) mx = s[k].buf > mx ? s[k].buf : mx;
         mx = warp_max(mx);
         if (mx != Real(0)) {
-            Real nrm[SPL], dev[SPL];
-            if constexpr (kParity) {
+            if constexpr (kParity) {  // np.var: mean, then mean of squared deviations, numpy summation order
+                Real nrm[SPL], dev[SPL];
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf / mx : Real(0);
-            } else {
-                const float inv = fast_rcp(mx);
+                const Real mean = sensor_sum<Real, SPL>(nrm, N, lane, ws.red, kSumNumpy) / (Real)N;
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) nrm[k] = s[k].active ? s[k].buf * inv : 0.f;
-            }
-            const Real mean = fdiv(sensor_sum<Real, SPL>(nrm, N, lane, ws.red, kSumNumpy), (Real)N);
+                for (int k = 0; k < SPL; ++k) {
+                    const Real d = nrm[k] - mean;
+                    dev[k] = s[k].active ? d * d : Real(0);
+                }
+                reward += p.p_starvation * (sensor_sum<Real, SPL>(dev, N, lane, ws.red, kSumNumpy) / (Real)N);
+            } else {  // one fused shuffle tree: var = E[x^2] - E[x]^2 on x in [0, 1]
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                const Real d = nrm[k] - mean;
-                dev[k] = s[k].active ? d * d : Real(0);
+                for (int k = 0; k < SPL; ++k) {
+                    const float v = s[k].active ? s[k].buf : 0.f;
+                    s1 += v;
+                    s2 = fmaf(v, v, s2);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    s1 += __shfl_xor_sync(kFull, s1, o);
+                    s2 += __shfl_xor_sync(kFull, s2, o);
+                }
+                const float inv = fast_rcp(mx), invn = fast_rcp((float)N);
+                const float mean = s1 * inv * invn;
+                reward += p.p_starvation * fmaxf(fmaf(s2 * inv * inv, invn, -mean * mean), 0.f);
             }
-            reward += p.p_starvation * fdiv(sensor_sum<Real, SPL>(dev, N, lane, ws.red, kSumNumpy), (Real)N);
         }
     }
     if (all_collected) reward += p.r_completion;

@@ -158,11 +158,76 @@ def generate(name, flavour):
         [int(blob["s%d/actions" % s].shape[0]) for s in sc["seeds"]][:6]))
 
 
+# --------------------------------------------------------------------------
+# DomainRandEnv sequences (dqn.py:177-451): several chained episodes per worker, auto-reset like DummyVecEnv.
+# Its layout / grid / start draws come from unseeded or global generators, so these fixtures DO store the
+# slot-addressed draw tables and the per-episode scenario.
+# --------------------------------------------------------------------------
+DR_SCENARIOS = {
+    "dr_stage4_n20": dict(n=20, stage=4, max_steps=70, steps=300, seed=11, p_collect=0.4),
+    "dr_stage2_n10": dict(n=10, stage=2, max_steps=50, steps=220, seed=12, p_collect=0.5),
+    "dr_stage4_n40": dict(n=40, stage=4, max_steps=60, steps=200, seed=13, p_collect=0.45),
+}
+DR_STEP_KEYS = ("reward", "truncated", "pos", "battery", "sf", "visited", "capture_triggers", "boundary_hits",
+                "edge_steps", "obs", "buf", "tx", "lost", "ema", "gen", "draws", "prev_dist", "first_cov",
+                "total_reward", "c_collision_count", "c_bytes_collected")
+DR_STAT_KEYS = ("total_generated", "total_collected", "total_lost", "battery_remaining", "ndr", "fairness_std",
+                "jains_index", "data_efficiency", "bytes_per_wh")
+
+
+def generate_domain_rand(name):
+    import random
+    sc = DR_SCENARIOS[name]
+    H.load_reference()
+    H.REC.normalise = True
+    cls, npx = H.load_domain_rand_env()
+    random.seed(sc["seed"])
+    np.random.seed(sc["seed"])
+    npx.layout_seed, npx.layout_calls = sc["seed"], 0
+    base = dict(max_steps=sc["max_steps"], path_loss_exponent=3.8, rssi_threshold=-85.0, sensor_duty_cycle=10.0,
+                max_battery=274.0, render_mode=None)
+    env = cls(fixed_num_sensors=sc["n"], curriculum_stage=sc["stage"], base_config=base)
+    rng = np.random.default_rng(sc["seed"])
+    blob, ep, steps, actions = {}, 0, [], []
+
+    def flush(first):
+        S = H.stack_steps(steps)
+        for k in DR_STEP_KEYS:
+            blob["e%d/%s" % (ep, k)] = S[k]
+        blob["e%d/actions" % ep] = np.array(actions, dtype=np.int8)
+        for k in ("grid", "positions", "start", "init_sf", "obs", "draws", "sf", "ema", "buf"):
+            blob["e%d/reset_%s" % (ep, k)] = first[k]
+
+    first = H.dr_traced_reset(env)
+    for t in range(sc["steps"]):
+        a = 4 if rng.random() < sc["p_collect"] else int(rng.integers(0, 4))
+        st = H.dr_traced_step(env, a)
+        steps.append(st)
+        actions.append(a)
+        if st["truncated"]:
+            flush(first)
+            first = H.dr_traced_reset(env)           # DummyVecEnv: reset right after the terminal step
+            les = env.last_episode_stats
+            blob["e%d/stats" % ep] = np.array([les[k] for k in DR_STAT_KEYS], dtype=np.float64)
+            blob["e%d/stats_ttc" % ep] = np.int32(-1 if les["time_to_coverage"] is None else les["time_to_coverage"])
+            ep, steps, actions = ep + 1, [], []
+    meta = dict(name=name, flavour="norm", n=sc["n"], stage=sc["stage"], episodes=ep, max_steps=sc["max_steps"],
+                stat_keys=list(DR_STAT_KEYS), numpy=np.__version__, python=platform.python_version(),
+                generator="oracle/gen_golden.py", reference_entry="src/agents/dqn/dqn.py::DomainRandEnv (exec'd slice)")
+    blob["meta"] = np.array(json.dumps(meta))
+    path = OUT / ("%s.norm.npz" % name)
+    np.savez_compressed(path, **blob)
+    print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
+
+
 RAW_TOO = ("c1_greedy_500_n20",)
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(SCENARIOS)
+    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS))
     for nm in names:
+        if nm in DR_SCENARIOS:
+            generate_domain_rand(nm)
+            continue
         generate(nm, "norm")
         if nm in RAW_TOO:
             generate(nm, "raw")

@@ -87,3 +87,71 @@ def test_cuda_reproduces_reference_golden(pkg, name, seeds, _):
             assert np.array_equal(obs[k], S["obs"][t]), tag      # and bit-exact vs the pinned oracle
     assert worst <= 1e-9, worst
     env.close()
+
+
+def test_cuda_reproduces_reference_domain_rand_sequences(pkg):
+    """The reference's DomainRandEnv sequences (tests/golden/dr_*.npz: chained episodes with per-episode grid,
+    layout, far start and inherited SF injected) replayed through the CUDA step with IN-KERNEL restarts:
+    three workers with N = 20 / 10 / 40 padded to 50 observation slots in one batch."""
+    import json
+    import torch
+    from golden_util import GOLDEN
+    names = ["dr_stage4_n20", "dr_stage2_n10", "dr_stage4_n40"]
+    Z = [np.load(GOLDEN / ("%s.norm.npz" % nm)) for nm in names]
+    M = [json.loads(str(z["meta"])) for z in Z]
+    E, P = len(names), 50
+    # max_steps differs per fixture, so each sequence gets its own single-env handle
+    worst = 0.0
+    for i, (z, m) in enumerate(zip(Z, M)):
+        n = m["n"]
+        g = lambda ep, k: z["e%d/%s" % (ep, k)]      # noqa: E731
+
+        def scen(ep):
+            xy = np.zeros((1, P, 2), dtype=np.float32)
+            xy[0, :n] = g(ep, "reset_positions")
+            dr = np.zeros((1, 6, P))
+            dr[0, :, :n] = np.nan_to_num(g(ep, "reset_draws"))
+            return dict(reset_sensor_xy=xy, reset_grid_wh=g(ep, "reset_grid")[None].astype(np.int32),
+                        reset_start_xy=g(ep, "reset_start")[None].astype(np.float32),
+                        reset_init_sf=np.array([int(g(ep, "reset_init_sf"))], dtype=np.int32), reset_draws=dr)
+        env = pkg.UAVVecEnv(1, num_sensors=n, max_sensors=P, obs_slots=50, domain_randomisation=True,
+                            precision="f64", rng="replay", auto_reset=True, max_steps=m["max_steps"])
+        env.set_replay(**scen(0))
+        obs = env.reset_tensors().cpu().numpy()
+        assert np.array_equal(obs[0], g(0, "reset_obs")), (names[i], "reset obs")
+        for ep in range(m["episodes"]):
+            acts = g(ep, "actions")
+            nxt = scen(ep + 1) if ep + 1 < m["episodes"] else scen(ep)
+            for t, a in enumerate(acts):
+                sd = np.zeros((1, 6, P))
+                sd[0, :, :n] = np.nan_to_num(g(ep, "draws")[t])
+                env.set_replay(step_draws=sd, **nxt)
+                env.step_tensors(torch.tensor([int(a)], dtype=torch.int32, device=env.device))
+                rew, done = float(env.reward[0]), bool(env.done[0])
+                tag = (names[i], ep, t)
+                assert done == bool(g(ep, "truncated")[t]), tag
+                ref = float(g(ep, "reward")[t])
+                err = abs(rew - ref) / max(abs(ref), 1.0)
+                worst = max(worst, err)
+                assert err <= 1e-9, (tag, rew, ref)
+                if not done:
+                    assert np.array_equal(env.obs.cpu().numpy()[0], g(ep, "obs")[t]), tag
+                    rec = env.records()[0]
+                    assert (rec["x"], rec["y"]) == tuple(g(ep, "pos")[t]) and rec["battery"] == g(ep, "battery")[t], tag
+                    assert rec["first_full_coverage_step"] == g(ep, "first_cov")[t], tag
+                    sf = env.state()["spreading_factor"].cpu().numpy()[0, :n]
+                    assert np.array_equal(sf, g(ep, "sf")[t]), tag
+                else:
+                    assert np.array_equal(env.terminal_obs.cpu().numpy()[0], g(ep, "obs")[t]), tag
+                    st = dict(zip(m["stat_keys"], g(ep, "stats")))
+                    es = dict(zip(("return", "length", "total_generated", "total_collected", "total_lost",
+                                   "battery_remaining", "ndr", "fairness_std", "jains_index"),
+                                  env.episode_stats.cpu().numpy()[0][:9]))
+                    for k in ("total_generated", "total_collected", "total_lost", "battery_remaining", "ndr",
+                              "fairness_std", "jains_index"):
+                        assert abs(es[k] - st[k]) <= 1e-9 * max(1.0, abs(st[k])), (tag, k, es[k], st[k])
+                    assert int(es["length"]) == len(acts)
+                    if ep + 1 < m["episodes"]:      # the in-kernel restart installed the next episode
+                        assert np.array_equal(env.obs.cpu().numpy()[0], g(ep + 1, "reset_obs")), tag
+        env.close()
+    assert worst <= 1e-9

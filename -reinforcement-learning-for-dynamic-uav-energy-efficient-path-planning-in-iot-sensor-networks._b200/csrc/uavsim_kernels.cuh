@@ -1298,7 +1298,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
 // (LDGSTS: no registers held, no stall until the data is needed), double buffered per warp.
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int SPL>
-struct alignas(16) StageBuf {
+struct alignas(alignof(SensorState<Real>)) StageBuf {
     SensorState<Real> st[32 * SPL];
     float2 pos[32 * SPL];
     Real gen[32 * SPL];
@@ -1426,7 +1426,7 @@ struct alignas(16) TileSmem {
 // Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
 // the tile block and (float32 layout) two stage buffers.
 template <typename Real, int SPL>
-struct alignas(16) StepWarpSmem {
+struct alignas(alignof(SensorState<Real>) > 16 ? alignof(SensorState<Real>) : 16) StepWarpSmem {
     WarpSmem ws;
     TileSmem<Real> ts;
     StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : 2];

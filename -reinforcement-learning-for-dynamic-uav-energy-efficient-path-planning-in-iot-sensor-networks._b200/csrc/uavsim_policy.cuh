@@ -1,0 +1,135 @@
+// On-device heuristic driver: NearestSensorGreedy of the reference
+// (src/agents/dqn/dqn_evaluation_results/greedy_agents.py:73-100 with GreedyAgent._move_toward :41-68),
+// batched: one warp per environment, sensors across lanes, reading the same state columns the step kernel
+// owns.  It is the driver of the reference's config-1 rollouts (sweep_eval.py:468-486) and of the curriculum's
+// greedy-benchmark gate (dqn.py:456-543), so evaluation no longer needs a per-environment Python loop.
+//
+//   1. COLLECT if any sensor with data is in range: `sensor.data_buffer > 0 and sensor.is_in_range(pos)`
+//      -- is_in_range draws a fresh shadowing value (iot_sensors.py:214-219); the reference stops probing at
+//      the first hit, which decides the same action as probing everyone.
+//   2. otherwise walk one cell toward the nearest sensor with data (float32 norm, first index on ties):
+//      COLLECT when within half a cell on both axes or when the move would leave the grid.
+//
+// Probe draws: REPLAY reads a table [E][P] (NaN = the reference never made that draw), PHILOX uses its own
+// stream id so the environment's draws are untouched.
+#pragma once
+#include "uavsim_kernels.cuh"
+
+namespace uavsim {
+
+constexpr uint32_t kStreamPolicy = 5;
+
+template <typename Real, bool REPLAY, int SPL>
+__global__ void __launch_bounds__(kThreads) nearest_greedy_kernel(const __grid_constant__ Params<Real> p,
+                                                                  const __grid_constant__ Buffers b,
+                                                                  const double* __restrict__ probe_draws,
+                                                                  int32_t* __restrict__ actions) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
+        const uavsim_env_record* R = b.rec + e;
+        const float ux = R->x, uy = R->y;
+        const int W = R->grid_w, H = R->grid_h, N = R->num_sensors;
+        Sensor<Real> s[SPL];
+        load_sensors<Real, SPL>(b, p, e, N, lane, s);
+        compute_det(p, ux, uy, s);
+
+        // 1. any sensor with data in range?
+        Real g[SPL];
+        if constexpr (REPLAY) {
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                g[k] = j < p.P ? (Real)probe_draws[(size_t)e * p.P + j] : Real(CUDART_NAN);
+            }
+        } else {
+            const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+            const Philox4 q = philox4x32_10((uint32_t)gid, ((uint32_t)(gid >> 32) & 0xffffffu) | (kStreamPolicy << 24),
+                                            R->episode, ((uint32_t)R->step << 8) | ((uint32_t)lane << 3), p.keys);
+            Real unused;
+            box_muller<Real>(q.x, q.y, p.sigma, g[0], unused);
+            if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, p.sigma, g[1], unused);
+        }
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) hit |= s[k].active && s[k].buf > Real(0) && (s[k].det + g[k]) >= p.thr;
+        int action = 4;
+        if (!__any_sync(kFull, hit)) {
+            // 2. nearest sensor with data: float32 norm, lowest index on ties (Python's min keeps the first)
+            float best = CUDART_INF_F;
+            int bi = -1;
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                if (s[k].active && s[k].buf > Real(0)) {
+                    const float dx = s[k].sx - ux, dy = s[k].sy - uy;
+                    const float d = sqrtf(dx * dx + dy * dy);
+                    if (d < best) {
+                        best = d;
+                        bi = lane + 32 * k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float od = __shfl_xor_sync(kFull, best, o);
+                const int oi = __shfl_xor_sync(kFull, bi, o);
+                if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
+                    best = od;
+                    bi = oi;
+                }
+            }
+            if (bi >= 0) {
+                float tx = 0.f, ty = 0.f;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const float sx = shfl(s[k].sx, bi & 31), sy = shfl(s[k].sy, bi & 31);
+                    if ((bi >> 5) == k) {
+                        tx = sx;
+                        ty = sy;
+                    }
+                }
+                const float dx = tx - ux, dy = ty - uy;
+                if (!(fabsf(dx) <= 0.5f && fabsf(dy) <= 0.5f)) {
+                    float nx = ux, ny = uy;
+                    if (fabsf(dx) > fabsf(dy))
+                        nx = ux + (dx > 0.f ? 1.0f : -1.0f);
+                    else
+                        ny = uy + (dy > 0.f ? 1.0f : -1.0f);
+                    if (!(nx < 0.f || nx >= (float)W || ny < 0.f || ny >= (float)H)) {
+                        const float mx = nx - ux, my = ny - uy;
+                        if (mx > 0.f)
+                            action = 3;  // RIGHT
+                        else if (mx < 0.f)
+                            action = 2;  // LEFT
+                        else if (my > 0.f)
+                            action = 0;  // UP
+                        else if (my < 0.f)
+                            action = 1;  // DOWN
+                    }
+                }
+            }
+        }
+        if (lane == 0) actions[e] = action;
+    }
+}
+
+template <typename Real>
+inline cudaError_t launch_nearest_greedy_t(const Params<Real>& p, const Buffers& b, const double* probe_draws,
+                                           int32_t* actions, bool replay, cudaStream_t st) {
+    const int grid = (b.E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int blocks = grid < 148 * 8 ? grid : 148 * 8;
+    const bool two = p.P > 32;
+    if (replay) {
+        if (two)
+            nearest_greedy_kernel<Real, true, 2><<<blocks, kThreads, 0, st>>>(p, b, probe_draws, actions);
+        else
+            nearest_greedy_kernel<Real, true, 1><<<blocks, kThreads, 0, st>>>(p, b, probe_draws, actions);
+    } else {
+        if (two)
+            nearest_greedy_kernel<Real, false, 2><<<blocks, kThreads, 0, st>>>(p, b, probe_draws, actions);
+        else
+            nearest_greedy_kernel<Real, false, 1><<<blocks, kThreads, 0, st>>>(p, b, probe_draws, actions);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace uavsim

@@ -312,6 +312,21 @@ class UAVVecEnv:
                                               _ptr(host["reward"]), _ptr(host["done"]), self._stream()))
         return host["obs"], host["reward"], host["done"]
 
+    def nearest_greedy_actions(self, probe_draws=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """NearestSensorGreedy.select_action (greedy_agents.py:73-100) for every env, on the device.  Returns an
+        int32 CUDA tensor [E] ready for `step_tensors`.  `probe_draws` ([E, P] float64, NaN = not drawn) is the
+        replay table of the agent's `is_in_range` probes; Philox mode draws its own."""
+        if out is None:
+            out = self._actions_dev
+        t = None
+        if probe_draws is not None:
+            t = probe_draws if isinstance(probe_draws, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(probe_draws))
+            t = t.to(device=self.device, dtype=torch.float64).contiguous()
+            assert tuple(t.shape) == (self.num_envs, self.cfg.max_sensors)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_policy_nearest_greedy(self._h, _ptr(out), _ptr(t), self._stream()))
+        return out
+
     def poll_errors(self):
         """Raises ValueError if any step since the last poll saw an action outside [0, 4]
         (uav_env.py:468).  Synchronises the stream."""

@@ -285,6 +285,13 @@ int uavsim_step(uavsim_handle* h, const int32_t* actions_dev, void* stream);
 int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_host, void* reward_host,
                      uint8_t* done_host, void* stream);
 
+/* ---- on-device heuristic driver ------------------------------- */
+/* NearestSensorGreedy.select_action for every env (greedy_agents.py:73-100, :41-68): COLLECT if a sensor with
+ * data is in range (one fresh shadowing draw per probe, iot_sensors.py:214-219), else one cell toward the nearest
+ * sensor with data.  actions_dev: [E] int32 out.  probe_draws_dev: replay mode only, [E][P] float64 shadowing
+ * values of the probes (NaN = not drawn); Philox mode draws from its own stream and takes NULL. */
+int uavsim_policy_nearest_greedy(uavsim_handle* h, int32_t* actions_dev, const double* probe_draws_dev, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------- */
 /* Synchronises `stream`, then reports and clears the device error word: returns
  * UAVSIM_ERR_INVALID_ACTION if any env saw an action outside [0,4] since the last poll

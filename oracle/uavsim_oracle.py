@@ -116,9 +116,12 @@ class StreamDraws:
 
     def burn_normals(self, k):
         """Consume k shadowing draws made by a caller outside the env (e.g. the
-        greedy driver's `is_in_range` calls, greedy_agents.py:85)."""
-        for _ in range(int(k)):
-            self._np.normal(0, self.sigma)
+        greedy driver's `is_in_range` calls, greedy_agents.py:85); returns them."""
+        return [float(self._np.normal(0, self.sigma)) for _ in range(int(k))]
+
+    def probe(self):
+        """One shadowing draw for a caller outside the env (not recorded in the slot table)."""
+        return float(self._np.normal(0, self.sigma))
 
 
 class SlotDraws:
@@ -546,6 +549,46 @@ class OracleEnv:
             capture_triggers=np.int32(self.capture_triggers),
             boundary_hits=np.int32(self.boundary_hits), edge_steps=np.int32(self.edge_steps),
             last_step_bytes=np.float64(self.last_step_bytes))
+
+
+def nearest_sensor_greedy(env: "OracleEnv", probe):
+    """Restatement of NearestSensorGreedy.select_action + GreedyAgent._move_toward
+    (src/agents/dqn/dqn_evaluation_results/greedy_agents.py:73-100, :41-68).
+    `probe(i)` returns the shadowing draw of `sensor_i.is_in_range` (one fresh draw per probe, made in index
+    order and only until the first hit).  Returns (action, probes) where probes[i] is the draw used for
+    sensor i (NaN = not probed)."""
+    thr = env.p["rssi_threshold"]
+    probes = np.full(env.n, np.nan)
+    det = env._det()
+    for i in range(env.n):                                  # :84-86
+        if env.buf[i] > 0:
+            probes[i] = probe(i)
+            if float(det[i] + probes[i]) >= thr:
+                return 4, probes
+    cand = [i for i in range(env.n) if env.buf[i] > 0]      # :94-100
+    if not cand:
+        return 4, probes
+    tgt = min(cand, key=lambda i: np.linalg.norm(env.spos[i] - env.pos))
+    ux, uy = env.pos[0], env.pos[1]                         # float32
+    dx, dy = env.spos[tgt, 0] - ux, env.spos[tgt, 1] - uy   # :43-45
+    if abs(dx) <= 0.5 and abs(dy) <= 0.5:
+        return 4, probes
+    if abs(dx) > abs(dy):
+        nx, ny = ux + (1 if dx > 0 else -1), uy
+    else:
+        nx, ny = ux, uy + (1 if dy > 0 else -1)
+    if nx < 0 or nx >= env.W or ny < 0 or ny >= env.H:      # :57-59
+        return 4, probes
+    mx, my = nx - ux, ny - uy
+    if mx > 0:
+        return 3, probes
+    if mx < 0:
+        return 2, probes
+    if my > 0:
+        return 0, probes
+    if my < 0:
+        return 1, probes
+    return 4, probes
 
 
 COLLECT_KEYS = ("bytes_collected", "was_new_sensor", "was_empty", "all_sensors_collected",

@@ -24,6 +24,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_STATE, ERR_INVALID_ACTION, ERR_UNSUPPORTED = 
 F64, F32 = 0, 1
 RNG_REPLAY, RNG_PHILOX = 0, 1
 RESET_FIXED, RESET_DOMAIN_RAND = 0, 1
+WRAP_NONE, WRAP_RELATIONAL = 0, 1
 SLOT_A, SLOT_B, SLOT_U, SLOT_C, SLOT_D, SLOT_E = range(6)
 FIELD_ENV_RECORD, FIELD_SENSOR_STATE, FIELD_SENSOR_POS, FIELD_SENSOR_GEN, FIELD_SENSOR_SF = range(5)
 
@@ -48,7 +49,7 @@ class Config(C.Structure):
         ("max_battery", _d), ("collection_duration", _d), ("start_x", _d), ("start_y", _d),
         ("tx_power_dbm", _d), ("noise_floor_dbm", _d), ("altitude_m", _d), ("adr_lambda", _d),
         ("shadowing_std_db", _d), ("capture_threshold_db", _d), ("power_move_w", _d), ("power_hover_w", _d),
-        ("init_sf", _i32), ("reserved0", _i32),
+        ("init_sf", _i32), ("wrapper", _i32),
         ("reward_per_byte", _d), ("reward_new_sensor", _d), ("reward_completion", _d),
         ("reward_urgency_reduction", _d), ("reward_movement", _d),
         ("penalty_revisit", _d), ("penalty_boundary", _d), ("penalty_collision", _d), ("penalty_battery", _d),
@@ -56,6 +57,8 @@ class Config(C.Structure):
         ("penalty_unvisited", _d), ("penalty_starved", _d), ("starvation_cr_threshold", _d),
         ("num_grids", _i32), ("grids", (_i32 * 2) * MAX_GRIDS),
         ("min_start_dist", _d), ("max_start_tries", _i32), ("reserved1", _i32), ("prox_eta", _d), ("jain_bonus", _d),
+        ("rel_gamma", _d), ("rel_dwell_bonus", _d), ("rel_reward_scale", _d), ("rel_dwell_steps", _i32),
+        ("rel_min_cluster", _i32),
     ]
 
 
@@ -77,7 +80,7 @@ class Scenario(C.Structure):
 
 class Replay(C.Structure):
     _fields_ = [("step_draws", C.c_void_p), ("reset_draws", C.c_void_p), ("reset_fill", C.c_void_p),
-                ("reset_init_sf", C.c_void_p), ("reset_scenario", Scenario)]
+                ("reset_init_sf", C.c_void_p), ("reset_scenario", Scenario), ("dwell_draws", C.c_void_p)]
 
 
 class FieldView(C.Structure):
@@ -94,7 +97,7 @@ class EnvRecord(C.Structure):
                 ("visited_lo", C.c_uint32), ("visited_hi", C.c_uint32), ("capture_triggers", _i32),
                 ("boundary_hits", _i32), ("edge_steps", _i32), ("collisions", _i32),
                 ("first_full_coverage_step", _i32), ("episode", C.c_uint32), ("delivered", _i32),
-                ("reserved", _i32 * 4)]
+                ("init_sf", _i32), ("dwell_steps", _i32), ("reserved", _i32 * 2)]
 
 
 assert C.sizeof(EnvRecord) == 128
@@ -107,7 +110,7 @@ ENV_RECORD_DTYPE = [
     ("grid_w", "<i4"), ("grid_h", "<i4"), ("num_sensors", "<i4"), ("visited_lo", "<u4"), ("visited_hi", "<u4"),
     ("capture_triggers", "<i4"), ("boundary_hits", "<i4"), ("edge_steps", "<i4"), ("collisions", "<i4"),
     ("first_full_coverage_step", "<i4"), ("episode", "<u4"), ("delivered", "<i4"), ("init_sf", "<i4"),
-    ("reserved", "<i4", (3,)),
+    ("dwell_steps", "<i4"), ("reserved", "<i4", (2,)),
 ]
 
 # Every symbol include/uavsim.h declares (tests/test_abi.py checks the header against this list).

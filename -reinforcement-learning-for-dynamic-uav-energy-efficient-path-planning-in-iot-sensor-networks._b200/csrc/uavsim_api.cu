@@ -77,6 +77,15 @@ int validate(const uavsim_config* c) {
     if (!(c->max_battery > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "max_battery must be > 0");
     if (!(c->collection_duration > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "collection_duration must be > 0");
     if (c->init_sf < 7 || c->init_sf > 12) return fail(UAVSIM_ERR_INVALID_ARG, "init_sf must be in [7, 12]");
+    if (c->wrapper != UAVSIM_WRAP_NONE && c->wrapper != UAVSIM_WRAP_RELATIONAL)
+        return fail(UAVSIM_ERR_INVALID_ARG, "wrapper must be UAVSIM_WRAP_NONE or UAVSIM_WRAP_RELATIONAL");
+    if (c->wrapper == UAVSIM_WRAP_RELATIONAL) {
+        if (c->features_per_sensor != 5)
+            return fail(UAVSIM_ERR_INVALID_ARG, "the relational wrapper needs features_per_sensor == 5 (env_wrapper.py:147)");
+        if (c->reset_mode != UAVSIM_RESET_FIXED)
+            return fail(UAVSIM_ERR_INVALID_ARG, "the relational wrapper sits on UAVEnvironment (UAVSIM_RESET_FIXED)");
+        if (c->rel_dwell_steps <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "rel_dwell_steps must be positive");
+    }
     if (c->reset_mode == UAVSIM_RESET_DOMAIN_RAND && c->rng_mode == UAVSIM_RNG_PHILOX) {
         if (c->num_grids <= 0 || c->num_grids > UAVSIM_MAX_GRIDS)
             return fail(UAVSIM_ERR_INVALID_ARG, "num_grids must be in [1, %d]", UAVSIM_MAX_GRIDS);
@@ -153,6 +162,12 @@ Params<Real> make_params(const uavsim_config& c) {
     p.cr_thr = (Real)c.starvation_cr_threshold;
     p.prox_eta = (Real)c.prox_eta;
     p.jain_bonus = (Real)c.jain_bonus;
+    p.relational = c.wrapper == UAVSIM_WRAP_RELATIONAL;
+    p.rel_dwell_steps = c.rel_dwell_steps;
+    p.rel_min_cluster = c.rel_min_cluster;
+    p.rel_gamma = (Real)c.rel_gamma;
+    p.rel_dwell_bonus = (Real)c.rel_dwell_bonus;
+    p.rel_scale = (Real)c.rel_reward_scale;
     p.max_battery = c.max_battery;
     p.batt_floor = 0.02 * c.max_battery;                       // uav.py:224
     p.e_move = (c.power_move_w * 1) / 3600;                    // uav.py:177-178
@@ -311,6 +326,12 @@ int uavsim_default_config(uavsim_config* c) {
     c->max_start_tries = 200;              // dqn.py:128
     c->prox_eta = 2.0;                     // dqn.py:129
     c->jain_bonus = 0.5;                   // dqn.py:442
+    c->wrapper = UAVSIM_WRAP_NONE;
+    c->rel_gamma = 0.99;                   // env_wrapper.py:48
+    c->rel_dwell_bonus = 25.0;             // env_wrapper.py:49
+    c->rel_reward_scale = 1e-5;            // env_wrapper.py:62
+    c->rel_dwell_steps = 10;               // env_wrapper.py:50
+    c->rel_min_cluster = 2;                // env_wrapper.py:51
     return UAVSIM_OK;
 }
 
@@ -526,6 +547,7 @@ int uavsim_set_replay(uavsim_handle* h, const uavsim_replay* rp) {
     b.rs_num_sensors = rp->reset_scenario.num_sensors;
     b.rs_grid_wh = rp->reset_scenario.grid_wh;
     b.rs_start_xy = rp->reset_scenario.start_xy;
+    b.dwell_draws = rp->dwell_draws;
     return UAVSIM_OK;
 }
 

@@ -73,6 +73,8 @@ struct Params {
     float inv_max_battery, inv_maxbuf, inv_rate;
     double min_start_dist;
     int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
+    int32_t relational, rel_dwell_steps, rel_min_cluster;  // RelationalUAVEnv wrapper (env_wrapper.py:47-62)
+    Real rel_gamma, rel_dwell_bonus, rel_scale;
     int32_t frame_k, frame_mirror;  // VecFrameStack: k frames; offset (floats) of the mirrored copy, 0 when k == 1
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     uint32_t key0, key1;
@@ -105,6 +107,7 @@ struct Buffers {
     const int32_t* rs_num_sensors;
     const int32_t* rs_grid_wh;
     const float* rs_start_xy;
+    const double* dwell_draws;  // [E][P] relational wrapper's range probes (replay)
     // bookkeeping
     double* stat_sums;
     unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
@@ -450,6 +453,21 @@ struct Draws {
             }
         }
     }
+    // RelationalUAVEnv._cluster_dwell_bonus: one is_in_range probe per sensor on a COLLECT step (env_wrapper.py:303)
+    __device__ __forceinline__ void dwell(const Params<Real>& p, const double* table, int lane, Real (&f)[SPL]) const {
+        if constexpr (REPLAY) {
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                f[k] = (table && j < p.P) ? (Real)table[j] : Real(0);
+            }
+        } else {
+            const Philox4 q = call(p, lane, 3);
+            Real unused;
+            box_muller<Real>(q.x, q.y, p.sigma, f[0], unused);
+            if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, p.sigma, f[1], unused);
+        }
+    }
     __device__ __forceinline__ Real winner(const Params<Real>& p, int lane, int k) const {
         const int j = lane + 32 * k;
         if constexpr (REPLAY) {
@@ -666,12 +684,33 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
             f[1] = (float)urg;
             f[2] = in_range ? link_quality_of<Real>(s[k].sf) : 0.0f;
             if constexpr (FPS == 5) {  // include_sensor_positions, uav_env.py:668-672
+                float rx, ry;
                 if constexpr (kParity) {
-                    f[3] = (float)(((double)s[k].sx - (double)h.x) / (double)h.W);
-                    f[4] = (float)(((double)s[k].sy - (double)h.y) / (double)h.H);
+                    double dx = ((double)s[k].sx - (double)h.x) / (double)h.W, dy = ((double)s[k].sy - (double)h.y) / (double)h.H;
+                    if (p.relational) {  // np.clip(., -1, 1), env_wrapper.py:217-218
+                        dx = dx < -1.0 ? -1.0 : (dx > 1.0 ? 1.0 : dx);
+                        dy = dy < -1.0 ? -1.0 : (dy > 1.0 ? 1.0 : dy);
+                    }
+                    rx = (float)dx;
+                    ry = (float)dy;
                 } else {
-                    f[3] = (s[k].sx - h.x) * inv_w;
-                    f[4] = (s[k].sy - h.y) * inv_h;
+                    rx = (s[k].sx - h.x) * inv_w;
+                    ry = (s[k].sy - h.y) * inv_h;
+                    if (p.relational) {
+                        rx = fminf(fmaxf(rx, -1.f), 1.f);
+                        ry = fminf(fmaxf(ry, -1.f), 1.f);
+                    }
+                }
+                if (p.relational) {  // Dict "sensors" row: [rel_x, rel_y, buffer, urgency, visited] (env_wrapper.py:216-222)
+                    const bool seen = j < 32 ? (h.vis_lo >> j) & 1u : (h.vis_hi >> (j - 32)) & 1u;
+                    f[2] = f[0];
+                    f[3] = f[1];
+                    f[0] = rx;
+                    f[1] = ry;
+                    f[4] = seen ? 1.0f : 0.0f;
+                } else {
+                    f[3] = rx;
+                    f[4] = ry;
                 }
             }
 #pragma unroll
@@ -690,6 +729,24 @@ __device__ __forceinline__ float nearest_with_data(float x, float y, const Senso
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         if (s[k].active && s[k].buf > Real(0)) {
+            const float dx = s[k].sx - x, dy = s[k].sy - y;
+            best = fminf(best, sqrtf(dx * dx + dy * dy));
+        }
+    }
+    best = warp_min(best);
+    return best == CUDART_INF_F ? 0.0f : best;
+}
+
+// RelationalUAVEnv._compute_potential (env_wrapper.py:270-289): float32 distance to the nearest UNVISITED
+// sensor, 0 when none is left; the potential is -dist / grid diagonal.
+template <typename Real, int SPL>
+__device__ __forceinline__ float nearest_unvisited(float x, float y, uint32_t vis_lo, uint32_t vis_hi, int lane,
+                                                   const Sensor<Real> (&s)[SPL]) {
+    float best = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const bool seen = k == 0 ? (vis_lo >> lane) & 1u : (vis_hi >> lane) & 1u;
+        if (s[k].active && !seen) {
             const float dx = s[k].sx - x, dy = s[k].sy - y;
             best = fminf(best, sqrtf(dx * dx + dy * dy));
         }
@@ -953,7 +1010,8 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
         __syncwarp();
         for (int i = lane; i < p.obs_dim; i += 32) out[i + p.frame_mirror] = out[i];
     }
-    const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s) : 0.f;
+    const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s)
+                                     : (p.relational ? nearest_unvisited(h.x, h.y, 0u, 0u, lane, s) : 0.f);
     __syncwarp();
     if (lane == 0) {
         R.x = h.x;
@@ -975,7 +1033,8 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
         R.capture_triggers = R.boundary_hits = R.edge_steps = R.collisions = R.delivered = 0;
         R.first_full_coverage_step = -1;
         R.episode = episode + 1;
-        R.reserved[0] = init_sf;
+        R.init_sf = init_sf;
+        R.dwell_steps = 0;
         if (b.action_mask) b.action_mask[e] = action_mask_of(h.x, h.y, W, H);
     }
     __syncwarp();
@@ -1445,11 +1504,11 @@ enum : int {
     kRX = 0, kRY = 1, kRStartX = 2, kRStartY = 3, kRBattery = 4, kRTotalReward = 6, kRTotalData = 8, kREpReturn = 10,
     kRLastBytes = 12, kRPrevDist = 13, kRElapsed = 14, kRStep = 15, kRGridW = 16, kRGridH = 17, kRN = 18, kRVisLo = 19,
     kRVisHi = 20, kRCapture = 21, kRBoundary = 22, kREdge = 23, kRCollisions = 24, kRFirstCov = 25, kREpisode = 26,
-    kRDelivered = 27
+    kRDelivered = 27, kRInitSf = 28, kRDwell = 29
 };
 static_assert(offsetof(uavsim_env_record, battery) == 4 * kRBattery && offsetof(uavsim_env_record, step) == 4 * kRStep &&
                   offsetof(uavsim_env_record, num_sensors) == 4 * kRN && offsetof(uavsim_env_record, episode) == 4 * kREpisode &&
-                  offsetof(uavsim_env_record, delivered) == 4 * kRDelivered && offsetof(uavsim_env_record, elapsed_s) == 4 * kRElapsed &&
+                  offsetof(uavsim_env_record, delivered) == 4 * kRDelivered && offsetof(uavsim_env_record, dwell_steps) == 4 * kRDwell && offsetof(uavsim_env_record, elapsed_s) == 4 * kRElapsed &&
                   offsetof(uavsim_env_record, total_reward) == 4 * kRTotalReward && offsetof(uavsim_env_record, episode_return) == 4 * kREpReturn &&
                   offsetof(uavsim_env_record, prev_dist_nearest) == 4 * kRPrevDist && offsetof(uavsim_env_record, first_full_coverage_step) == 4 * kRFirstCov,
               "record word map out of date");
@@ -1558,8 +1617,28 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
         h.H = ts.H[k];
         h.N = N;
         h.battery = 0.0;
+        h.vis_lo = collect ? ts.nvis_lo[k] : ts.vis_lo[k];  // relational rows carry the visited flag
+        h.vis_hi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
         observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL>(p, b, ts, k, e), lane,
                                                        obs_frame(p, b, e));
+    }
+
+    // ---- RelationalUAVEnv.step supplements (env_wrapper.py:169-198): potential distance, dwell probes ----
+    if (FPS == 5 && p.relational) {
+        const uint32_t vlo = collect ? ts.nvis_lo[k] : ts.vis_lo[k], vhi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
+        const float dist = nearest_unvisited(ts.x[k], ts.y[k], vlo, vhi, lane, s);
+        int n_in = 0;
+        if (collect) {
+            Real f[SPL];
+            step_draws<Real, REPLAY, SPL>(p, b, ts, k, e).dwell(p, b.dwell_draws ? b.dwell_draws + (size_t)e * p.P : nullptr, lane, f);
+#pragma unroll
+            for (int k2 = 0; k2 < SPL; ++k2)
+                n_in += __popc(__ballot_sync(kFull, s[k2].active && (s[k2].det + f[k2]) >= p.thr));
+        }
+        if (lane == 0) {
+            ts.cur_dist[k] = dist;
+            ts.counts[k] |= n_in << 24;
+        }
     }
 
     // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
@@ -1794,6 +1873,35 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                     R.set_f(kRPrevDist, curd);
                     if (R.i32(kRFirstCov) < 0 && (__popc(vis_lo) + __popc(vis_hi)) == N) R.set_i(kRFirstCov, ts.step[lane]);
                     if (flags & kFlagJain) shaped += fdiv(p.jain_bonus * (ts.jain[lane] - Real(0.5)), (Real)N);
+                }
+                if (FPS == 5 && p.relational) {  // env_wrapper.py:169-198, :291-313
+                    const double W = ts.W[lane], H = ts.H[lane];
+                    const double diag = sqrt(W * W + H * H);
+                    const float prev = R.f(kRPrevDist), curd = ts.cur_dist[lane];
+                    R.set_f(kRPrevDist, curd);
+                    int dwell = R.i32(kRDwell);
+                    const int n_in = (ts.counts[lane] >> 24) & 0x7f;
+                    Real bonus = Real(0);
+                    if (!collect) {
+                        dwell = 0;
+                    } else if (n_in >= p.rel_min_cluster && dwell < p.rel_dwell_steps) {
+                        if constexpr (kParity)
+                            bonus = p.rel_dwell_bonus * (1.0 - (double)dwell / p.rel_dwell_steps);
+                        else
+                            bonus = p.rel_dwell_bonus * (1.0f - (float)dwell / (float)p.rel_dwell_steps);
+                        dwell += 1;
+                    } else if (n_in < p.rel_min_cluster) {
+                        dwell = 0;
+                    }
+                    R.set_i(kRDwell, dwell);
+                    if constexpr (kParity) {
+                        const double shaping = p.rel_gamma * (-(double)curd / diag) - (-(double)prev / diag);
+                        shaped = (reward + shaping + bonus) * p.rel_scale;
+                    } else {
+                        const float inv = (float)(1.0 / diag);
+                        const float shaping = p.rel_gamma * (-curd * inv) + prev * inv;
+                        shaped = (reward + shaping + bonus) * p.rel_scale;
+                    }
                 }
                 // commit the record (uav_env.py:487 and the counters of :300-307)
                 const float x = ts.x[lane], y = ts.y[lane];

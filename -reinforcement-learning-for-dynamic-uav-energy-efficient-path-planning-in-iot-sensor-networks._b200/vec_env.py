@@ -70,7 +70,7 @@ class UAVVecEnv:
                  reward_movement=10.0, include_sensor_positions=False,
                  # batched-simulator arguments
                  max_sensors: Optional[int] = None, obs_slots: Optional[int] = None, n_stack: int = 1,
-                 domain_randomisation=False, curriculum_stage=0,
+                 domain_randomisation=False, curriculum_stage=0, relational=False,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
                  device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
         if render_mode is not None:
@@ -88,6 +88,13 @@ class UAVVecEnv:
         cfg.max_sensors = P
         cfg.obs_slots = int(obs_slots if obs_slots is not None else
                             (MAX_SENSORS_LIMIT if domain_randomisation and P <= MAX_SENSORS_LIMIT else P))
+        # RelationalUAVEnv (env_wrapper.py:110-161) forces include_sensor_positions=True and pads to n_max = 50
+        self.relational = bool(relational)
+        if relational:
+            include_sensor_positions = True
+            cfg.wrapper = N.WRAP_RELATIONAL
+            if obs_slots is None and P <= MAX_SENSORS_LIMIT:
+                cfg.obs_slots = MAX_SENSORS_LIMIT
         cfg.features_per_sensor = 5 if include_sensor_positions else 3
         cfg.frame_stack = int(n_stack)          # VecFrameStack(n_stack) on device (dqn.py:1098,1278)
         cfg.precision = {"f64": N.F64, "f32": N.F32}[precision]
@@ -245,7 +252,8 @@ class UAVVecEnv:
             self._num_sensors = np.asarray(num_sensors, dtype=np.int32).copy()
 
     def set_replay(self, step_draws=None, reset_draws=None, reset_fill=None, reset_init_sf=None,
-                   reset_sensor_xy=None, reset_num_sensors=None, reset_grid_wh=None, reset_start_xy=None):
+                   reset_sensor_xy=None, reset_num_sensors=None, reset_grid_wh=None, reset_start_xy=None,
+                   dwell_draws=None):
         """Bind slot-addressed draw tables (device float64 tensors or numpy arrays); see
         include/uavsim.h `uavsim_replay`.  Arguments left None keep their previous binding."""
         dev = self.device
@@ -266,10 +274,13 @@ class UAVVecEnv:
         rn = up("rs_n", reset_num_sensors, torch.int32)
         rg = up("rs_g", reset_grid_wh, torch.int32)
         rs = up("rs_s", reset_start_xy, torch.float32)
+        dw = up("dwell", dwell_draws, torch.float64)
+        assert dw is None or tuple(dw.shape) == (E, P)
         for t in (sd, rd):
             assert t is None or tuple(t.shape) == (E, N.NUM_SLOTS, P), "draw tables are [E, 6, P]"
         assert rf is None or tuple(rf.shape) == (E, P)
-        rp = N.Replay(_ptr(sd), _ptr(rd), _ptr(rf), _ptr(ri), N.Scenario(_ptr(rxy), _ptr(rn), _ptr(rg), _ptr(rs)))
+        rp = N.Replay(_ptr(sd), _ptr(rd), _ptr(rf), _ptr(ri), N.Scenario(_ptr(rxy), _ptr(rn), _ptr(rg), _ptr(rs)),
+                      _ptr(dw))
         N.check(self.lib.uavsim_set_replay(self._h, C.byref(rp)))
 
     # ------------------------------------------------------------------ zero-copy tensor API
@@ -326,6 +337,19 @@ class UAVVecEnv:
         with torch.cuda.device(self.device):
             N.check(self.lib.uavsim_policy_nearest_greedy(self._h, _ptr(out), _ptr(t), self._stream()))
         return out
+
+    def relational_obs(self) -> dict:
+        """The Dict observation of RelationalUAVEnv (env_wrapper.py:149-160, 200-228) as zero-copy views of the
+        bound row: "uav" [E,3], "sensors" [E,n_max,5] = [rel_x, rel_y, buffer, urgency, visited], and the static
+        "mask" [E,n_max] (1 = real sensor slot)."""
+        if not self.relational:
+            raise RuntimeError("constructed without relational=True")
+        slots = int(self.cfg.obs_slots)
+        row = self.obs[:, -self.dims.obs_dim:]          # newest frame when stacked
+        if getattr(self, "_rel_mask", None) is None:
+            n = torch.as_tensor(self._num_sensors, device=self.device)
+            self._rel_mask = (torch.arange(slots, device=self.device)[None, :] < n[:, None]).float()
+        return {"uav": row[:, :3], "sensors": row[:, 3:].unflatten(1, (slots, 5)), "mask": self._rel_mask}
 
     def poll_errors(self):
         """Raises ValueError if any step since the last poll saw an action outside [0, 4]

@@ -64,6 +64,14 @@ typedef enum uavsim_reset_mode {
                                     far-start rejection sampling, proximity + Jain shaping (dqn.py:301-444) */
 } uavsim_reset_mode;
 
+typedef enum uavsim_wrapper {
+    UAVSIM_WRAP_NONE = 0,
+    UAVSIM_WRAP_RELATIONAL = 1 /* RelationalUAVEnv (env_wrapper.py:110-313): needs features_per_sensor == 5; the observation
+                                  row becomes uav(3) + obs_slots x [rel_x, rel_y, buffer, urgency, visited] (the Dict's
+                                  "uav" and "sensors" entries back to back; "mask" is slot < N), and the reward
+                                  (base + potential shaping + cluster dwell bonus) * rel_reward_scale */
+} uavsim_wrapper;
+
 /* Replay draw slots.  A/B/U are consumed per sensor with data on a COLLECT
  * step (ADR draw, link-probability draw, duty-cycle uniform), C by each SF-group
  * winner (range check in collect_data), D/E per sensor by every observation
@@ -110,7 +118,7 @@ typedef struct uavsim_config {
     double power_move_w;         /* 500 */
     double power_hover_w;        /* 700 */
     int32_t init_sf;             /* 12: IoTSensor.reset forces SF12 (iot_sensors.py:309) */
-    int32_t reserved0;
+    int32_t wrapper;             /* uavsim_wrapper: observation / reward wrapper applied on top of the step */
 
     /* --- RewardFunction (reward_function.py:7-44 with the overrides of uav_env.py:339-344) --- */
     double reward_per_byte, reward_new_sensor, reward_completion, reward_urgency_reduction, reward_movement;
@@ -125,6 +133,13 @@ typedef struct uavsim_config {
     int32_t reserved1;
     double prox_eta;                     /* 2.0 */
     double jain_bonus;                   /* 0.5: reward += jain_bonus*(J-0.5)/N */
+
+    /* --- RelationalUAVEnv (experiments/relational_policy/env_wrapper.py:47-62), wrapper == UAVSIM_WRAP_RELATIONAL --- */
+    double rel_gamma;                    /* 0.99: shaping = gamma*Phi(s') - Phi(s), Phi = -dist(nearest unvisited)/diagonal */
+    double rel_dwell_bonus;              /* 25: cluster dwell bonus at dwell step 0, decaying linearly */
+    double rel_reward_scale;             /* 1e-5 */
+    int32_t rel_dwell_steps;             /* 10 */
+    int32_t rel_min_cluster;             /* 2 in-range sensors */
 } uavsim_config;
 
 /* State columns visible through uavsim_get_field (structure-of-arrays in HBM). */
@@ -146,7 +161,7 @@ typedef struct uavsim_env_record {
     double total_data_collected;
     double episode_return;      /* what Monitor would report: base reward + DomainRandEnv shaping */
     float last_step_bytes;
-    float prev_dist_nearest;    /* DomainRandEnv._prev_dist_nearest */
+    float prev_dist_nearest;    /* DomainRandEnv._prev_dist_nearest; relational wrapper: distance behind _prev_potential */
     float elapsed_s;            /* sum of step durations this episode */
     int32_t step;               /* current_step */
     int32_t grid_w, grid_h;
@@ -159,7 +174,9 @@ typedef struct uavsim_env_record {
     int32_t first_full_coverage_step; /* -1 = not yet (dqn.py:428-431) */
     uint32_t episode;           /* episodes completed by this env (RNG counter word) */
     int32_t delivered;          /* cumulative successful transmissions (iot_sensors.py:141-143) */
-    int32_t reserved[4];
+    int32_t init_sf;            /* SF the episode's sensors started with (12, or the inherited one of DomainRandEnv) */
+    int32_t dwell_steps;        /* RelationalUAVEnv._dwell_steps */
+    int32_t reserved[2];
 } uavsim_env_record;
 
 typedef struct uavsim_field_view {
@@ -240,6 +257,8 @@ typedef struct uavsim_replay {
     const double* reset_fill;
     const int32_t* reset_init_sf;
     uavsim_scenario reset_scenario;
+    const double* dwell_draws; /* [E][P]: shadowing values of the relational wrapper's is_in_range probes on a COLLECT step
+                                  (env_wrapper.py:303), nullable unless wrapper == UAVSIM_WRAP_RELATIONAL */
 } uavsim_replay;
 
 typedef struct uavsim_handle uavsim_handle;

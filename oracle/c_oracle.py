@@ -25,8 +25,10 @@ _PARAM_DOUBLES = (
     "reward_new_sensor", "reward_completion", "reward_urgency_reduction", "reward_movement",
     "penalty_revisit", "penalty_boundary", "penalty_collision", "penalty_battery", "penalty_hover",
     "penalty_step", "penalty_data_loss", "penalty_starvation", "penalty_unvisited",
-    "penalty_starved", "starvation_cr_threshold", "prox_eta", "jain_bonus")
-_PARAM_INTS = ("max_steps", "init_sf", "features_per_sensor", "obs_slots", "domain_rand", "reserved")
+    "penalty_starved", "starvation_cr_threshold", "prox_eta", "jain_bonus", "rel_gamma", "rel_dwell_bonus",
+    "rel_reward_scale")
+_PARAM_INTS = ("max_steps", "init_sf", "features_per_sensor", "obs_slots", "domain_rand", "relational",
+               "rel_dwell_steps", "rel_min_cluster")
 
 
 class OrcParams(C.Structure):
@@ -39,7 +41,7 @@ ENV_DTYPE = np.dtype([
     ("battery", "f8"), ("total_reward", "f8"), ("total_data_collected", "f8"),
     ("episode_return", "f8"), ("last_step_bytes", "f8"), ("prev_dist_nearest", "f8"),
     ("capture_triggers", "i4"), ("boundary_hits", "i4"), ("edge_steps", "i4"), ("collisions", "i4"),
-    ("first_full_coverage_step", "i4"), ("delivered", "i4"),
+    ("first_full_coverage_step", "i4"), ("delivered", "i4"), ("dwell_steps", "i4"), ("pad0", "i4"),
     ("spx", "f4", (MAXS,)), ("spy", "f4", (MAXS,)),
     ("buf", "f8", (MAXS,)), ("gen", "f8", (MAXS,)), ("tx", "f8", (MAXS,)), ("lost", "f8", (MAXS,)),
     ("ema", "f8", (MAXS,)), ("cur", "f8", (MAXS,)),
@@ -69,7 +71,8 @@ def lib():
     return _lib
 
 
-def make_params(params: dict, obs_slots: int, domain_rand=False, prox_eta=2.0, jain_bonus=0.5) -> OrcParams:
+def make_params(params: dict, obs_slots: int, domain_rand=False, prox_eta=2.0, jain_bonus=0.5,
+                relational=False) -> OrcParams:
     """`params` uses the key names of uavsim_oracle.default_params()."""
     p = OrcParams()
     for k in _PARAM_DOUBLES:
@@ -81,6 +84,12 @@ def make_params(params: dict, obs_slots: int, domain_rand=False, prox_eta=2.0, j
     p.features_per_sensor = 5 if params.get("include_sensor_positions") else 3
     p.obs_slots = int(obs_slots)
     p.domain_rand = int(bool(domain_rand))
+    # RelationalUAVEnv constants (env_wrapper.py:47-62); the wrapper forces include_sensor_positions=True
+    p.relational = int(bool(relational))
+    p.rel_gamma, p.rel_dwell_bonus, p.rel_reward_scale = 0.99, 25.0, 1e-5
+    p.rel_dwell_steps, p.rel_min_cluster = 10, 2
+    if relational:
+        p.features_per_sensor = 5
     return p
 
 
@@ -91,11 +100,11 @@ def _ptr(a, ct):
 class COracleBatch:
     """E independent envs stepped by the C oracle.  Draw tables are [E, 6, P] float64."""
 
-    def __init__(self, params: dict, E: int, P: int, obs_slots=None, domain_rand=False, threads=1):
+    def __init__(self, params: dict, E: int, P: int, obs_slots=None, domain_rand=False, threads=1, relational=False):
         self.lib = lib()
         self.E, self.P = int(E), int(P)
         self.obs_slots = int(obs_slots if obs_slots is not None else P)
-        self.p = make_params(params, self.obs_slots, domain_rand)
+        self.p = make_params(params, self.obs_slots, domain_rand, relational=relational)
         self.envs = np.zeros(self.E, dtype=ENV_DTYPE)
         self.obs_dim = 3 + self.p.features_per_sensor * self.obs_slots
         self.obs = np.zeros((self.E, self.obs_dim), dtype=np.float32)
@@ -140,13 +149,14 @@ class COracleBatch:
             run(0, self.E)
         return self.obs
 
-    def step(self, actions, draws, want_detail=True):
+    def step(self, actions, draws, want_detail=True, dwell=None):
         actions = np.ascontiguousarray(actions, dtype=np.int32)
         draws = np.ascontiguousarray(draws, dtype=np.float64)
+        dwell = None if dwell is None else np.ascontiguousarray(dwell, dtype=np.float64)
 
         def run(a, b):
             return self.lib.orc_step_batch(C.byref(self.p), C.c_void_p(self.envs.ctypes.data), a, b,
-                                           _ptr(actions, C.c_int32), _ptr(draws, C.c_double), self.P,
+                                           _ptr(actions, C.c_int32), _ptr(draws, C.c_double), _ptr(dwell, C.c_double), self.P,
                                            _ptr(self.obs, C.c_float), _ptr(self.reward, C.c_double),
                                            _ptr(self.done, C.c_uint8), _ptr(self.mask, C.c_uint8),
                                            _ptr(self.detail, C.c_double) if want_detail else None)

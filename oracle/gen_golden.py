@@ -220,13 +220,67 @@ def generate_domain_rand(name):
     print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
 
 
+# --------------------------------------------------------------------------
+# RelationalUAVEnv sequences (env_wrapper.py:110-313): Dict observation + potential shaping + dwell bonus.
+# --------------------------------------------------------------------------
+REL_SCENARIOS = {
+    "rel_300_n20": dict(grid=(300, 300), n=20, seed=21, steps=260, p_collect=0.55, start=(150.0, 150.0),
+                        kwargs=dict(max_steps=130, max_battery=274.0)),
+    "rel_150_n35": dict(grid=(150, 150), n=35, seed=22, steps=200, p_collect=0.7, start=(70.0, 80.0),
+                        kwargs=dict(max_steps=100, max_battery=274.0)),
+}
+REL_STEP_KEYS = ("reward", "truncated", "pos", "battery", "sf", "visited", "obs", "buf", "tx", "lost", "ema", "gen",
+                 "draws", "dwell_draws", "potential", "dwell_steps", "total_reward", "m_ndr", "m_jains", "m_efficiency")
+
+
+def generate_relational(name):
+    import random
+    sc = REL_SCENARIOS[name]
+    H.load_reference()
+    H.REC.normalise = True
+    cls = H.load_relational_env()
+    random.seed(sc["seed"])
+    np.random.seed(sc["seed"])
+    env = cls(grid_size=sc["grid"], num_sensors=sc["n"], n_max=50, uav_start_position=sc["start"],
+              path_loss_exponent=3.8, rssi_threshold=-85.0, sensor_duty_cycle=10.0, **sc["kwargs"])
+    rng = np.random.default_rng(sc["seed"])
+    blob, ep, steps, actions = {}, 0, [], []
+    first = H.rel_traced_reset(env, seed=sc["seed"])
+    blob["positions"] = np.array(env.sensor_positions, dtype=np.float64)
+    for t in range(sc["steps"]):
+        a = 4 if rng.random() < sc["p_collect"] else int(rng.integers(0, 4))
+        st = H.rel_traced_step(env, a)
+        steps.append(st)
+        actions.append(a)
+        if st["truncated"]:
+            S = H.stack_steps(steps)
+            for k in REL_STEP_KEYS:
+                blob["e%d/%s" % (ep, k)] = S[k]
+            blob["e%d/actions" % ep] = np.array(actions, dtype=np.int8)
+            for k in ("obs", "mask", "draws", "fill", "sf", "ema", "buf", "potential"):
+                blob["e%d/reset_%s" % (ep, k)] = first[k]
+            first = H.rel_traced_reset(env)
+            ep, steps, actions = ep + 1, [], []
+    meta = dict(name=name, flavour="norm", grid=list(sc["grid"]), n=sc["n"], start=list(sc["start"]), episodes=ep,
+                env_kwargs=sc["kwargs"], numpy=np.__version__, python=platform.python_version(),
+                generator="oracle/gen_golden.py",
+                reference_entry="src/experiments/relational_policy/env_wrapper.py::RelationalUAVEnv")
+    blob["meta"] = np.array(json.dumps(meta))
+    path = OUT / ("%s.norm.npz" % name)
+    np.savez_compressed(path, **blob)
+    print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
+
+
 RAW_TOO = ("c1_greedy_500_n20",)
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS))
+    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS) + list(REL_SCENARIOS))
     for nm in names:
         if nm in DR_SCENARIOS:
             generate_domain_rand(nm)
+            continue
+        if nm in REL_SCENARIOS:
+            generate_relational(nm)
             continue
         generate(nm, "norm")
         if nm in RAW_TOO:

@@ -49,8 +49,8 @@ import numpy as np
 REFERENCE_ROOT = Path(os.environ.get("UAVSIM_REFERENCE_ROOT", "/root/reference"))
 _STUBS = Path(__file__).resolve().parent / "_stubs"
 
-SLOT_A, SLOT_B, SLOT_U, SLOT_C, SLOT_D, SLOT_E = range(6)
-NUM_SLOTS = 6
+SLOT_A, SLOT_B, SLOT_U, SLOT_C, SLOT_D, SLOT_E, SLOT_F = range(7)
+NUM_SLOTS = 7   # F: RelationalUAVEnv's dwell-bonus range probes (env_wrapper.py:303); fixtures of the base env keep A..E
 
 
 def reference_available() -> bool:
@@ -208,7 +208,7 @@ def load_reference():
         return o_gsp(self, uav_position, use_advanced_model)
 
     def iir(self, uav_position):
-        REC.ctx = (self.sensor_id, SLOT_E)
+        REC.ctx = (self.sensor_id, SLOT_E if REC.in_obs else SLOT_F)
         return o_iir(self, uav_position)
 
     def obs(self):
@@ -316,7 +316,7 @@ def traced_reset(env, seed=None):
         REC.end()
     st = snapshot(env)
     st["obs"] = np.asarray(obs, dtype=np.float32)
-    st["draws"] = REC.draws.copy()
+    st["draws"] = REC.draws[:6].copy()
     st["fill"] = np.array(REC.fill, dtype=np.float64)
     st["info"] = info
     return st
@@ -333,7 +333,8 @@ def traced_step(env, action):
     st["reward"] = np.float64(reward)
     st["truncated"] = np.bool_(truncated)
     st["terminated"] = np.bool_(terminated)
-    st["draws"] = REC.draws.copy()
+    st["draws"] = REC.draws[:6].copy()
+    st["dwell_draws"] = REC.draws[6].copy()
     ck = REC.collect_kwargs
     for k in COLLECT_KEYS:
         st["c_" + k] = np.float64(ck[k]) if ck is not None else np.float64(np.nan)
@@ -427,7 +428,7 @@ def dr_traced_reset(env):
         REC.end()
     st = snapshot(env)
     st["obs"] = np.asarray(obs, dtype=np.float32)
-    st["draws"] = REC.draws.copy()
+    st["draws"] = REC.draws[:6].copy()
     st["grid"] = np.array(env.grid_size, dtype=np.int32)
     st["positions"] = np.array(env.sensor_positions, dtype=np.float64)
     st["start"] = np.asarray(env.uav.start_position, dtype=np.float32).copy()
@@ -441,4 +442,60 @@ def dr_traced_step(env, action):
     st["prev_dist"] = np.float64(env._prev_dist_nearest)
     ffc = env._first_full_coverage_step
     st["first_cov"] = np.int32(-1 if ffc is None else ffc)
+    return st
+
+
+# --------------------------------------------------------------------------
+# RelationalUAVEnv (src/experiments/relational_policy/env_wrapper.py:110-313)
+# --------------------------------------------------------------------------
+def load_relational_env():
+    mods = load_reference()
+    if "RelationalUAVEnv" not in mods:
+        load_greedy_agents()       # `environment.*` aliases
+        p = str(REFERENCE_ROOT / "src" / "experiments" / "relational_policy")
+        if p not in sys.path:
+            sys.path.insert(0, p)
+        import env_wrapper
+        mods["relational"] = env_wrapper
+        mods["RelationalUAVEnv"] = env_wrapper.RelationalUAVEnv
+    return mods["RelationalUAVEnv"]
+
+
+def rel_flat(obs: dict) -> np.ndarray:
+    """uav(3) + sensors(n_max,5) flattened: the row layout the batched simulator writes in relational mode."""
+    return np.concatenate([obs["uav"], obs["sensors"].reshape(-1)]).astype(np.float32)
+
+
+def rel_traced_reset(env, seed=None):
+    REC.fill = []
+    REC.begin(env.num_sensors)
+    try:
+        obs, info = env.reset(seed=seed)
+    finally:
+        REC.end()
+    st = snapshot(env)
+    st["obs"] = rel_flat(obs)
+    st["mask"] = np.asarray(obs["mask"], dtype=np.float32)
+    st["draws"] = REC.draws[:6].copy()
+    st["fill"] = np.array(REC.fill, dtype=np.float64)
+    st["potential"] = np.float64(env._prev_potential)
+    return st
+
+
+def rel_traced_step(env, action):
+    REC.begin(env.num_sensors)
+    try:
+        obs, reward, terminated, truncated, info = env.step(int(action))
+    finally:
+        REC.end()
+    st = snapshot(env)
+    st["obs"] = rel_flat(obs)
+    st["reward"] = np.float64(reward)
+    st["truncated"] = np.bool_(truncated)
+    st["draws"] = REC.draws[:6].copy()
+    st["dwell_draws"] = REC.draws[6].copy()
+    st["potential"] = np.float64(env._prev_potential)
+    st["dwell_steps"] = np.int32(env._dwell_steps)
+    for k in ("ndr", "jains", "efficiency"):
+        st["m_" + k] = np.float64(info.get(k, np.nan))
     return st

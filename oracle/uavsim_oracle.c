@@ -21,6 +21,8 @@
  *   rewards/reward_function.py:46-57 :59-67 :69-79 :81-128
  *   environment/uav_env.py:376-394 :400-427 :429-488 :494-516 :518-632 :638-674
  *   agents/dqn/dqn.py:301-372 (DomainRandEnv.reset) :405-444 (shaping) :446-451 (Jain)
+ *   experiments/relational_policy/env_wrapper.py:163-228 (reset/step/Dict observation) :270-313
+ *       (potential shaping, cluster dwell bonus)
  *
  * Float discipline: the reference mixes float32 geometry with float64 everything
  * else; every expression below keeps the reference's type and association, and the
@@ -53,7 +55,9 @@ typedef struct orc_params {
     double penalty_data_loss, penalty_starvation, penalty_unvisited, penalty_starved,
         starvation_cr_threshold;
     double prox_eta, jain_bonus;
-    int32_t max_steps, init_sf, features_per_sensor, obs_slots, domain_rand, reserved;
+    double rel_gamma, rel_dwell_bonus, rel_reward_scale; /* env_wrapper.py:47-62 */
+    int32_t max_steps, init_sf, features_per_sensor, obs_slots, domain_rand, relational;
+    int32_t rel_dwell_steps, rel_min_cluster;
 } orc_params;
 
 typedef struct orc_env {
@@ -62,7 +66,7 @@ typedef struct orc_env {
     double battery, total_reward, total_data_collected, episode_return, last_step_bytes;
     double prev_dist_nearest;
     int32_t capture_triggers, boundary_hits, edge_steps, collisions, first_full_coverage_step,
-        delivered;
+        delivered, dwell_steps, pad0;
     float spx[ORC_MAXS], spy[ORC_MAXS];
     double buf[ORC_MAXS], gen[ORC_MAXS], tx[ORC_MAXS], lost[ORC_MAXS], ema[ORC_MAXS], cur[ORC_MAXS];
     int8_t sf[ORC_MAXS];
@@ -230,6 +234,47 @@ static double dist_nearest_with_data(const orc_env* e) {
     return any ? (double)best : 0.0;
 }
 
+/* env_wrapper.py:270-289: distance (float32 norm) to the nearest UNVISITED sensor, 0 when all are visited;
+ * the potential is -dist / grid_diagonal. */
+static float nearest_unvisited(const orc_env* e) {
+    int any = 0;
+    float best = 0.f;
+    for (int i = 0; i < e->N; i++) {
+        if (e->visited[i]) continue;
+        float dx = e->spx[i] - e->x, dy = e->spy[i] - e->y;
+        float d = sqrtf(dx * dx + dy * dy);
+        if (!any || d < best) best = d;
+        any = 1;
+    }
+    return any ? best : 0.f;
+}
+static double potential_of(const orc_env* e, float dist) {
+    double diag = sqrt((double)((long)e->W * e->W + (long)e->H * e->H));
+    return -(double)dist / diag;
+}
+
+/* env_wrapper.py:200-228: row = uav(3) then per slot [rel_x, rel_y, buffer, urgency, visited]; the mask is
+ * (slot < N) and is not part of the row.  No draws, no ADR. */
+static void observe_relational(const orc_params* p, const orc_env* e, float* obs) {
+    double W = (double)e->W, H = (double)e->H, ux = (double)e->x, uy = (double)e->y;
+    int dim = 3 + 5 * p->obs_slots;
+    for (int k = 0; k < dim; k++) obs[k] = 0.0f;
+    obs[0] = (float)(ux / W);
+    obs[1] = (float)(uy / H);
+    obs[2] = (float)(e->battery / p->max_battery);
+    for (int i = 0; i < e->N; i++) {
+        double rx = ((double)e->spx[i] - ux) / W, ry = ((double)e->spy[i] - uy) / H;
+        rx = rx < -1.0 ? -1.0 : (rx > 1.0 ? 1.0 : rx);
+        ry = ry < -1.0 ? -1.0 : (ry > 1.0 ? 1.0 : ry);
+        float* o = obs + 3 + 5 * i;
+        o[0] = (float)rx;
+        o[1] = (float)ry;
+        o[2] = (float)(e->buf[i] / p->max_buffer_size);
+        o[3] = (float)urgency(p, e, i);
+        o[4] = e->visited[i] ? 1.0f : 0.0f;
+    }
+}
+
 static uint8_t action_mask(const orc_env* e) { /* derived from uav.py:175 */
     float x = e->x, y = e->y;
     uint8_t m = 1u << 4;
@@ -274,8 +319,13 @@ void orc_reset_env(const orc_params* p, orc_env* e, const double* fill, const do
     e->last_step_bytes = 0.0;
     e->capture_triggers = e->boundary_hits = e->edge_steps = e->collisions = e->delivered = 0;
     e->first_full_coverage_step = -1;
-    observe(p, e, draws, P, obs);
+    observe(p, e, draws, P, obs); /* the parent builds (and draws for) its flat observation in every mode */
     e->prev_dist_nearest = dist_nearest_with_data(e);
+    if (p->relational) { /* env_wrapper.py:163-167 */
+        observe_relational(p, e, obs);
+        e->dwell_steps = 0;
+        e->prev_dist_nearest = (double)nearest_unvisited(e);
+    }
     if (mask) *mask = action_mask(e);
 }
 
@@ -453,8 +503,8 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
  * base reward, plus DomainRandEnv shaping in domain_rand mode.  Invalid action -> returns -1 and
  * leaves the env untouched (the reference raises ValueError, uav_env.py:468, after having aged the
  * sensors; callers validate first, as the host wrapper does). */
-int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draws, int P, float* obs,
-                 double* reward_out, uint8_t* mask, double* detail) {
+int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draws, const double* dwell, int P,
+                 float* obs, double* reward_out, uint8_t* mask, double* detail) {
     if (action < 0 || action > 4) return -1;
     if (detail)
         for (int k = 0; k < D_COUNT; k++) detail[k] = 0.0;
@@ -521,6 +571,32 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
             shaped += p->jain_bonus * (j - 0.5) / e->N;
         }
     }
+    if (p->relational) { /* env_wrapper.py:169-198 */
+        double phi_s = potential_of(e, (float)prev_dist);
+        float nd = nearest_unvisited(e);
+        double phi_n = potential_of(e, nd);
+        e->prev_dist_nearest = (double)nd;
+        double shaping = p->rel_gamma * phi_n - phi_s;
+        double bonus = 0.0;
+        if (action != 4) { /* :291-313 */
+            e->dwell_steps = 0;
+        } else {
+            int n_in = 0;
+            for (int i = 0; i < e->N; i++) {
+                double det = det_rssi(p, e->x, e->y, e->spx[i], e->spy[i]);
+                n_in += (det + dwell[i]) >= p->rssi_threshold;
+            }
+            if (n_in >= p->rel_min_cluster && e->dwell_steps < p->rel_dwell_steps) {
+                double frac = 1.0 - (double)e->dwell_steps / p->rel_dwell_steps;
+                bonus = p->rel_dwell_bonus * frac;
+                e->dwell_steps += 1;
+            } else if (n_in < p->rel_min_cluster) {
+                e->dwell_steps = 0;
+            }
+        }
+        shaped = (r + shaping + bonus) * p->rel_reward_scale;
+        observe_relational(p, e, obs);
+    }
     e->episode_return += shaped;
     *reward_out = shaped;
     if (mask) *mask = action_mask(e);
@@ -544,13 +620,14 @@ void orc_reset_batch(const orc_params* p, orc_env* envs, int e0, int e1, const d
 
 /* Returns the number of invalid actions. */
 int orc_step_batch(const orc_params* p, orc_env* envs, int e0, int e1, const int32_t* actions,
-                   const double* draws, int P, float* obs, double* reward, uint8_t* done, uint8_t* mask,
-                   double* detail) {
+                   const double* draws, const double* dwell, int P, float* obs, double* reward, uint8_t* done,
+                   uint8_t* mask, double* detail) {
     int dim = 3 + p->features_per_sensor * p->obs_slots;
     int bad = 0;
     for (int e = e0; e < e1; e++) {
-        int t = orc_step_env(p, &envs[e], actions[e], draws + (size_t)e * ORC_SLOTS * P, P,
-                             obs + (size_t)e * dim, &reward[e], mask ? mask + e : NULL,
+        int t = orc_step_env(p, &envs[e], actions[e], draws + (size_t)e * ORC_SLOTS * P,
+                             dwell ? dwell + (size_t)e * P : NULL, P, obs + (size_t)e * dim, &reward[e],
+                             mask ? mask + e : NULL,
                              detail ? detail + (size_t)e * D_COUNT : NULL);
         if (t < 0)
             bad++;

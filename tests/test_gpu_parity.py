@@ -133,3 +133,13 @@ def test_float32_throughput_build_on_replayed_draws(pkg):
     res = run_parity_case(pkg, E=2048, N=20, grid=(500, 500), steps=24, seed=53, p_collect=0.3, precision="f32")
     frac = res["discrete_mismatches"] / (res["steps"] * 20)
     assert frac < 1e-3, res
+
+
+def test_config2_full_episodes_to_truncation(pkg):
+    """configs[1] over WHOLE episodes: 1024 envs, uniform random actions until every env has truncated
+    (battery-limited, ~1790 steps) and restarted in-kernel; state compared every 64 steps."""
+    from parity_util import run_parity_case
+    res = run_parity_case(pkg, E=1024, N=20, grid=(500, 500), steps=1900, seed=61, p_collect=0.2, auto_reset=True,
+                          compare_every=64)
+    _check(res)
+    assert res["dones"] >= 1024, res

@@ -10,7 +10,11 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libuavsim.so"
+import os
+
+# UAVSIM_LIB: developer override used for A/B runs of kernel variants (tools/build_variants.py); the product
+# library is libuavsim.so next to this file.
+LIB_PATH = Path(os.environ["UAVSIM_LIB"]).resolve() if os.environ.get("UAVSIM_LIB") else PKG / "libuavsim.so"
 
 MAX_SENSORS = 64
 MAX_GRIDS = 8
@@ -139,7 +143,7 @@ def load() -> C.CDLL:
         return _lib
     from . import build as _build
     try:
-        path = _build.build()
+        path = LIB_PATH if os.environ.get("UAVSIM_LIB") else _build.build()
     except Exception as exc:  # no nvcc on this box: use the shipped binary if there is one
         if not LIB_PATH.exists():
             raise ImportError("libuavsim.so is missing and could not be built: %s" % exc) from exc

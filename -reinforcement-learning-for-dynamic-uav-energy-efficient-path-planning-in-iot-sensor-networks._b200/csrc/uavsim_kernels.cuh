@@ -1048,13 +1048,26 @@ constexpr int min_blocks_per_sm() {
 // Block shape of the step kernel.  The one-slot-per-lane kernel fits 80 registers: 8 warps x 3 blocks per
 // SM.  The two-slot kernel needs ~100 registers to stay out of local memory (with most of the SM given to
 // shared memory the L1 is small, so a spill is an L2 round trip): 10 warps x 2 blocks per SM.
+// (the UAVSIM_W*/B* macros exist for block-shape sweeps: tools/build_variants.py)
+#ifndef UAVSIM_W2
+#define UAVSIM_W2 10
+#endif
+#ifndef UAVSIM_B2
+#define UAVSIM_B2 2
+#endif
+#ifndef UAVSIM_W1
+#define UAVSIM_W1 8
+#endif
+#ifndef UAVSIM_B1
+#define UAVSIM_B1 3
+#endif
 template <typename Real, int SPL>
 __host__ __device__ constexpr int step_warps() {
-    return (!std::is_same<Real, double>::value && SPL == 2) ? 10 : 8;
+    return std::is_same<Real, double>::value ? 8 : (SPL == 2 ? UAVSIM_W2 : UAVSIM_W1);
 }
 template <typename Real, int SPL>
 __host__ __device__ constexpr int step_min_blocks() {
-    return std::is_same<Real, double>::value ? 1 : (SPL == 2 ? 2 : 3);
+    return std::is_same<Real, double>::value ? 1 : (SPL == 2 ? UAVSIM_B2 : UAVSIM_B1);
 }
 
 template <typename Real, bool REPLAY, int SPL, int FPS>
@@ -1104,18 +1117,38 @@ __device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& i
 template <typename Real>
 struct TileSmem;
 
+// LEAN instantiations of the step kernel compile the optional features out (DomainRandEnv shaping, the
+// relational wrapper, draw export, parity diagnostics): the plain UAVEnvironment step -- the benchmarked
+// configuration -- then carries neither their uniform branches nor their code in its instruction stream.
+template <bool LEAN, typename Real>
+__device__ __forceinline__ bool feat_domain_rand(const Params<Real>& p) {
+    if constexpr (LEAN) return false; else return p.domain_rand != 0;
+}
+template <bool LEAN, typename Real>
+__device__ __forceinline__ bool feat_relational(const Params<Real>& p) {
+    if constexpr (LEAN) return false; else return p.relational != 0;
+}
+template <bool LEAN>
+__device__ __forceinline__ double* feat_step_detail(const Buffers& b) {
+    if constexpr (LEAN) return nullptr; else return b.step_detail;
+}
+template <bool LEAN>
+__device__ __forceinline__ void* feat_draw_export(const Buffers& b) {
+    if constexpr (LEAN) return nullptr; else return b.draw_export;
+}
+
 // Draws of the step in flight for slot k of the tile, rebuilt at each point of use (cheap) so that nothing
 // of it stays live across the step.
-template <typename Real, bool REPLAY, int SPL>
+template <typename Real, bool REPLAY, int SPL, bool LEAN>
 __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
                                                                 const TileSmem<Real>& ts, int k, int e);
 
 // UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment (slot k of the tile).
 // Results go to the tile block (and the parity diagnostics) from lane 0.
-template <typename Real, bool REPLAY, int SPL>
+template <typename Real, bool REPLAY, int SPL, bool LEAN>
 __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
                                                int k, int e, Sensor<Real> (&s)[SPL], Real step_loss, int lane) {
-    const Draws<Real, REPLAY, SPL> dr = step_draws<Real, REPLAY, SPL>(p, b, ts, k, e);
+    const Draws<Real, REPLAY, SPL> dr = step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e);
     Hot h;
     h.N = ts.N[k];
     h.elapsed = ts.elapsed[k];
@@ -1334,8 +1367,8 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
         ts.counts[k] = collisions | (captures << 8) | (delivered << 12);
         ts.nvis_lo[k] = h.vis_lo;
         ts.nvis_hi[k] = h.vis_hi;
-        if (b.step_detail) {  // parity diagnostics: the collect step's intermediates (phase C adds the rest)
-            double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+        if (feat_step_detail<LEAN>(b)) {  // parity diagnostics: the collect step's intermediates (phase C adds the rest)
+            double* d = feat_step_detail<LEAN>(b) + (size_t)e * UAVSIM_DETAIL_COUNT;
             d[UAVSIM_DETAIL_COLLISIONS] = collisions;
             d[UAVSIM_DETAIL_BYTES] = (double)total_bytes;
             d[UAVSIM_DETAIL_URGENCY_REDUCED] = (double)urg_red;
@@ -1463,7 +1496,10 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
 // over the tile).  The phases talk through a small structure-of-arrays block in shared memory; the tile's
 // 128-byte records sit in shared memory with a 4-byte XOR swizzle so that both the coalesced global
 // copies (lane = word) and the per-lane field accesses (lane = environment) are bank-conflict free.
-constexpr int kTile = 16;
+#ifndef UAVSIM_TILE
+#define UAVSIM_TILE 16
+#endif
+constexpr int kTile = UAVSIM_TILE;
 
 template <typename Real>
 struct alignas(16) TileSmem {
@@ -1528,7 +1564,7 @@ struct RecView {  // lane-private access to record l of the swizzled tile
     }
 };
 
-template <typename Real, bool REPLAY, int SPL>
+template <typename Real, bool REPLAY, int SPL, bool LEAN>
 __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
                                                                 const TileSmem<Real>& ts, int k, int e) {
     const uint64_t gid = (uint64_t)(p.env_id_offset + e);
@@ -1538,8 +1574,9 @@ __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real
     dr.episode = ts.episode[k] - 1;  // the record counts resets done; the running episode is one less
     dr.step = (uint32_t)ts.step[k];
     dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
-    dr.exp = (!REPLAY && b.draw_export) ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
-                                        : nullptr;
+    dr.exp = (!REPLAY && feat_draw_export<LEAN>(b))
+                 ? reinterpret_cast<Real*>(feat_draw_export<LEAN>(b)) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
+                 : nullptr;
     return dr;
 }
 
@@ -1558,7 +1595,7 @@ __device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* acti
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
 // the environment are read from the tile block where they are used and results are written back as soon as
 // they exist, so that little besides the sensor registers is live across the phase.
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN>
 __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
                                              int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
     constexpr bool kParity = std::is_same<Real, double>::value;
@@ -1566,8 +1603,8 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     const bool collect = flags & kFlagCollect;
     const int N = ts.N[k];
 
-    if (!REPLAY && b.draw_export) {
-        Real* exp = reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P;
+    if (!REPLAY && feat_draw_export<LEAN>(b)) {
+        Real* exp = reinterpret_cast<Real*>(feat_draw_export<LEAN>(b)) + (size_t)e * UAVSIM_NUM_SLOTS * p.P;
         const Real nan = Real(CUDART_NAN);
         for (int i = lane; i < UAVSIM_NUM_SLOTS * p.P; i += 32) exp[i] = nan;
         __syncwarp();
@@ -1594,7 +1631,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     }
 
     compute_det(p, ts.x[k], ts.y[k], s);  // the UAV has already moved (phase A)
-    if (collect) collect_action<Real, REPLAY, SPL>(p, b, ts, ws, k, e, s, step_loss, lane);
+    if (collect) collect_action<Real, REPLAY, SPL, LEAN>(p, b, ts, ws, k, e, s, step_loss, lane);
 
     if (flags & kFlagTruncated) {  // reward_function.py:59-67 (counted only when the episode ends this step)
         int starved = 0;
@@ -1619,18 +1656,18 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
         h.battery = 0.0;
         h.vis_lo = collect ? ts.nvis_lo[k] : ts.vis_lo[k];  // relational rows carry the visited flag
         h.vis_hi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
-        observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL>(p, b, ts, k, e), lane,
+        observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e), lane,
                                                        obs_frame(p, b, e));
     }
 
     // ---- RelationalUAVEnv.step supplements (env_wrapper.py:169-198): potential distance, dwell probes ----
-    if (FPS == 5 && p.relational) {
+    if (FPS == 5 && feat_relational<LEAN>(p)) {
         const uint32_t vlo = collect ? ts.nvis_lo[k] : ts.vis_lo[k], vhi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
         const float dist = nearest_unvisited(ts.x[k], ts.y[k], vlo, vhi, lane, s);
         int n_in = 0;
         if (collect) {
             Real f[SPL];
-            step_draws<Real, REPLAY, SPL>(p, b, ts, k, e).dwell(p, b.dwell_draws ? b.dwell_draws + (size_t)e * p.P : nullptr, lane, f);
+            step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e).dwell(p, b.dwell_draws ? b.dwell_draws + (size_t)e * p.P : nullptr, lane, f);
 #pragma unroll
             for (int k2 = 0; k2 < SPL; ++k2)
                 n_in += __popc(__ballot_sync(kFull, s[k2].active && (s[k2].det + f[k2]) >= p.thr));
@@ -1642,7 +1679,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     }
 
     // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
-    if (p.domain_rand) {
+    if (feat_domain_rand<LEAN>(p)) {
         const float cur_dist = nearest_with_data(ts.x[k], ts.y[k], s);
         const float elapsed = ts.elapsed[k];
         Real r1[SPL], r2[SPL];
@@ -1673,7 +1710,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN = false>
 __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<Real, SPL>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
@@ -1824,7 +1861,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                 if (!(ts.flags[k] & kFlagValid)) continue;
                 load_sensors<Real, SPL>(b, p, e, ts.N[k], lane, s);
             }
-            sensor_phase<Real, REPLAY, SPL, FPS, STACK>(p, b, ts, ws, k, e, lane, s);
+            sensor_phase<Real, REPLAY, SPL, FPS, STACK, LEAN>(p, b, ts, ws, k, e, lane, s);
         }
         __syncwarp();
 
@@ -1862,7 +1899,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                 }
                 // DomainRandEnv.step shaping (dqn.py:415-444)
                 Real shaped = reward;
-                if (p.domain_rand) {
+                if (feat_domain_rand<LEAN>(p)) {
                     const float prev = R.f(kRPrevDist), curd = ts.cur_dist[lane];
                     if (prev > 0.f) {
                         if constexpr (kParity)
@@ -1874,7 +1911,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                     if (R.i32(kRFirstCov) < 0 && (__popc(vis_lo) + __popc(vis_hi)) == N) R.set_i(kRFirstCov, ts.step[lane]);
                     if (flags & kFlagJain) shaped += fdiv(p.jain_bonus * (ts.jain[lane] - Real(0.5)), (Real)N);
                 }
-                if (FPS == 5 && p.relational) {  // env_wrapper.py:169-198, :291-313
+                if (FPS == 5 && feat_relational<LEAN>(p)) {  // env_wrapper.py:169-198, :291-313
                     const double W = ts.W[lane], H = ts.H[lane];
                     const double diag = sqrt(W * W + H * H);
                     const float prev = R.f(kRPrevDist), curd = ts.cur_dist[lane];
@@ -1949,8 +1986,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                     o[p.frame_mirror + 2] = f2;
                 }
                 if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(x, y, ts.W[lane], ts.H[lane]);
-                if (b.step_detail) {
-                    double* d = b.step_detail + (size_t)e * UAVSIM_DETAIL_COUNT;
+                if (feat_step_detail<LEAN>(b)) {
+                    double* d = feat_step_detail<LEAN>(b) + (size_t)e * UAVSIM_DETAIL_COUNT;
                     if (!collect)  // a collect step's intermediates were written by phase B
                         for (int i = 0; i < UAVSIM_DETAIL_BASE_REWARD; ++i) d[i] = 0.0;
                     d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;

@@ -55,6 +55,30 @@ template <typename Real>
 inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const int32_t* actions, bool replay,
                                  cudaStream_t st) {
     const bool two = p.P > 32;
+    // the plain UAVEnvironment step without optional features runs the LEAN instantiation (throughput build)
+    const bool lean = !std::is_same<Real, double>::value && !replay && !p.domain_rand && !p.relational &&
+                      !b.draw_export && !b.step_detail && p.fps == 3
+#ifdef UAVSIM_NO_LEAN
+                      && false
+#endif
+        ;
+    if constexpr (!std::is_same<Real, double>::value) {
+        if (lean) {
+            const bool stack = p.frame_k > 1;
+            if (two) {
+                constexpr size_t smem = step_smem_bytes<Real, 2>();
+                constexpr int warps = step_warps<Real, 2>();
+                auto k = stack ? step_kernel<Real, false, 2, 3, true, true> : step_kernel<Real, false, 2, 3, false, true>;
+                k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
+            } else {
+                constexpr size_t smem = step_smem_bytes<Real, 1>();
+                constexpr int warps = step_warps<Real, 1>();
+                auto k = stack ? step_kernel<Real, false, 1, 3, true, true> : step_kernel<Real, false, 1, 3, false, true>;
+                k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
+            }
+            return cudaGetLastError();
+        }
+    }
 #define UAVSIM_LAUNCH_STEP(R, S)                                                              \
     do {                                                                                      \
         constexpr size_t smem = step_smem_bytes<Real, S>();                                   \

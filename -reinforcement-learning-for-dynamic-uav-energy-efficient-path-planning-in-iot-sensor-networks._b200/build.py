@@ -2,7 +2,7 @@
 
 Three translation units:
   csrc/uavsim_f64.cu  parity kernels      -fmad=false (no FMA contraction; see uavsim_kernels.cuh)
-  csrc/uavsim_f32.cu  throughput kernels  default contraction, MUFU intrinsics are explicit
+  csrc/uavsim_f32.cu  throughput kernels  --use_fast_math (FMA contraction, flush-to-zero, approximate div/sqrt)
   csrc/uavsim_api.cu  C-ABI + host logic
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box.
 """
@@ -25,7 +25,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(CSRC)]
 UNITS = {
     "uavsim_f64.cu": ["-fmad=false"],
-    "uavsim_f32.cu": [],
+    "uavsim_f32.cu": ["--use_fast_math"],   # flush-to-zero MUFU sequences, approximate div/sqrt: tolerance build
     "uavsim_api.cu": [],
 }
 

@@ -123,7 +123,7 @@ SYMBOLS = (
     "uavsim_create", "uavsim_destroy", "uavsim_bind_outputs", "uavsim_get_field", "uavsim_set_scenario",
     "uavsim_generate_layouts", "uavsim_set_replay", "uavsim_set_stage_grids", "uavsim_reset", "uavsim_step",
     "uavsim_step_host", "uavsim_poll_error", "uavsim_stat_sums", "uavsim_launch_count", "uavsim_frame_slot",
-    "uavsim_policy_nearest_greedy",
+    "uavsim_policy_nearest_greedy", "uavsim_policy_max_throughput_greedy",
 )
 
 
@@ -170,6 +170,7 @@ def load() -> C.CDLL:
     lib.uavsim_launch_count.argtypes = [vp]
     lib.uavsim_launch_count.restype = C.c_int64
     lib.uavsim_policy_nearest_greedy.argtypes = [vp, vp, vp, vp]
+    lib.uavsim_policy_max_throughput_greedy.argtypes = [vp, vp, vp, vp]
     lib.uavsim_frame_slot.argtypes = [vp]
     lib.uavsim_frame_slot.restype = C.c_int
     if lib.uavsim_abi_version() != 1:

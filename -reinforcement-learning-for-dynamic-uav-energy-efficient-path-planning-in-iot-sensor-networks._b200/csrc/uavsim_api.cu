@@ -622,6 +622,20 @@ int uavsim_policy_nearest_greedy(uavsim_handle* h, int32_t* actions_dev, const d
     return UAVSIM_OK;
 }
 
+int uavsim_policy_max_throughput_greedy(uavsim_handle* h, int32_t* actions_dev, const double* probe_draws_dev,
+                                        void* stream) {
+    if (!h || !actions_dev) return fail(UAVSIM_ERR_INVALID_ARG, "handle/actions is NULL");
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    if (replay && !probe_draws_dev) return fail(UAVSIM_ERR_STATE, "replay mode: probe_draws is required");
+    if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
+    cudaError_t e = h->cfg.precision == UAVSIM_F64
+                        ? launch_max_throughput_greedy_f64(h->p64, h->buf, probe_draws_dev, actions_dev, replay, (cudaStream_t)stream)
+                        : launch_max_throughput_greedy_f32(h->p32, h->buf, probe_draws_dev, actions_dev, replay, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "max_throughput_greedy_kernel launch");
+    h->launches += 1;
+    return UAVSIM_OK;
+}
+
 int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_host, void* reward_host,
                      uint8_t* done_host, void* stream) {
     if (!h || !actions_host || !reward_host || !done_host)

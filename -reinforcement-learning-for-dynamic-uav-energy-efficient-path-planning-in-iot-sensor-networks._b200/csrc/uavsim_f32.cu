@@ -16,4 +16,8 @@ cudaError_t launch_nearest_greedy_f32(const Params<float>& p, const Buffers& b, 
                                       int32_t* actions, bool replay, cudaStream_t st) {
     return launch_nearest_greedy_t<float>(p, b, probe_draws, actions, replay, st);
 }
+cudaError_t launch_max_throughput_greedy_f32(const Params<float>& p, const Buffers& b, const double* probe_draws,
+                                              int32_t* actions, bool replay, cudaStream_t st) {
+    return launch_max_throughput_greedy_t<float>(p, b, probe_draws, actions, replay, st);
+}
 }  // namespace uavsim

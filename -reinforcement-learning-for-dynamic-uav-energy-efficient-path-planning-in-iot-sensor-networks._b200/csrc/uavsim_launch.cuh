@@ -21,6 +21,11 @@ cudaError_t launch_nearest_greedy_f64(const Params<double>& p, const Buffers& b,
 cudaError_t launch_nearest_greedy_f32(const Params<float>& p, const Buffers& b, const double* probe_draws,
                                       int32_t* actions, bool replay, cudaStream_t st);
 
+cudaError_t launch_max_throughput_greedy_f64(const Params<double>& p, const Buffers& b, const double* probe_draws,
+                                              int32_t* actions, bool replay, cudaStream_t st);
+cudaError_t launch_max_throughput_greedy_f32(const Params<float>& p, const Buffers& b, const double* probe_draws,
+                                              int32_t* actions, bool replay, cudaStream_t st);
+
 // Persistent grid: one wave of blocks at full residency (SM count x occupancy), never more blocks than
 // there are groups of kWarpsPerBlock environments.
 template <typename Kernel>

@@ -327,6 +327,14 @@ class UAVVecEnv:
         """NearestSensorGreedy.select_action (greedy_agents.py:73-100) for every env, on the device.  Returns an
         int32 CUDA tensor [E] ready for `step_tensors`.  `probe_draws` ([E, P] float64, NaN = not drawn) is the
         replay table of the agent's `is_in_range` probes; Philox mode draws its own."""
+        return self._policy_actions(self.lib.uavsim_policy_nearest_greedy, probe_draws, out)
+
+    def max_throughput_greedy_actions(self, probe_draws=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """MaxThroughputGreedyV2.select_action (greedy_agents.py:105-200) for every env, on the device; same
+        conventions as `nearest_greedy_actions`."""
+        return self._policy_actions(self.lib.uavsim_policy_max_throughput_greedy, probe_draws, out)
+
+    def _policy_actions(self, entry, probe_draws, out):
         if out is None:
             out = self._actions_dev
         t = None
@@ -335,7 +343,7 @@ class UAVVecEnv:
             t = t.to(device=self.device, dtype=torch.float64).contiguous()
             assert tuple(t.shape) == (self.num_envs, self.cfg.max_sensors)
         with torch.cuda.device(self.device):
-            N.check(self.lib.uavsim_policy_nearest_greedy(self._h, _ptr(out), _ptr(t), self._stream()))
+            N.check(entry(self._h, _ptr(out), _ptr(t), self._stream()))
         return out
 
     def relational_obs(self) -> dict:

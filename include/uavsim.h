@@ -310,6 +310,12 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
  * sensor with data.  actions_dev: [E] int32 out.  probe_draws_dev: replay mode only, [E][P] float64 shadowing
  * values of the probes (NaN = not drawn); Philox mode draws from its own stream and takes NULL. */
 int uavsim_policy_nearest_greedy(uavsim_handle* h, int32_t* actions_dev, const double* probe_draws_dev, void* stream);
+/* MaxThroughputGreedyV2.select_action for every env (greedy_agents.py:105-200): COLLECT if a sensor with data is
+ * in range (every sensor with data is probed, :133-138) and its spreading factor is within the adaptive threshold
+ * (:188-197); else one cell toward the sensor maximising SF priority + buffer fill + duty cycle - distance
+ * (:155-182).  Same argument conventions as uavsim_policy_nearest_greedy. */
+int uavsim_policy_max_throughput_greedy(uavsim_handle* h, int32_t* actions_dev, const double* probe_draws_dev,
+                                        void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------- */
 /* Synchronises `stream`, then reports and clears the device error word: returns

@@ -62,12 +62,22 @@ def _policy_greedy(env):
     return pick
 
 
+def _policy_max_throughput(env):
+    agent = H.load_greedy_agents().MaxThroughputGreedyV2(env)
+
+    def pick(env_, obs, t):
+        return int(agent.select_action(obs))
+    return pick
+
+
 def run_episode(sc, seed):
     kw = dict(sc.get("env_kwargs", {}))
     env = H.make_env(sc["grid"], sc["n"], seed=seed, start=sc.get("start"), **kw)
     first = H.traced_reset(env, seed=seed)
     if sc["policy"] == "greedy":
         pick = _policy_greedy(env)
+    elif sc["policy"] == "max_throughput":
+        pick = _policy_max_throughput(env)
     else:
         pick = _policy_random(seed, sc.get("p_collect"))
     steps, actions, burn = [], [], []
@@ -94,6 +104,12 @@ def run_episode(sc, seed):
            "reset_obs": first["obs"], "reset_fill": first["fill"], "reset_sf": first["sf"],
            "reset_ema": first["ema"], "reset_buf": first["buf"],
            "draws_head": np.concatenate([first["draws"][None], S["draws"][:DRAW_SAMPLE_STEPS]])}
+    if sc.get("slim"):      # driver fixtures: the env is pinned elsewhere; keep what pins the AGENT
+        for k in ("reward", "truncated", "pos", "c_bytes_collected"):
+            out[k] = S[k]
+        for k in ("positions", "reset_obs", "reset_sf", "reset_ema", "reset_buf", "draws_head", "sparse_idx"):
+            out.pop(k)
+        return out
     for k in DENSE_KEYS + ("obs_sum",):
         out[k] = S[k]
     for k in SPARSE_KEYS:
@@ -104,6 +120,11 @@ def run_episode(sc, seed):
 SCENARIOS = {
     # config 1: the reference's own CPU-runnable case
     "c1_greedy_500_n20": dict(grid=(500, 500), n=20, policy="greedy", steps=None, seeds=list(range(20))),
+    # MaxThroughputGreedyV2 (greedy_agents.py:105-200) driving the same configuration: pins the restated driver
+    "c1_maxtp_500_n20": dict(grid=(500, 500), n=20, policy="max_throughput", steps=None, seeds=list(range(8)),
+                             slim=True),
+    "maxtp_200_n30": dict(grid=(200, 200), n=30, policy="max_throughput", steps=None, seeds=[0, 1, 2],
+                          start=(100.0, 100.0), slim=True, env_kwargs=dict(max_battery=60.0)),
     # config 2 episodes (per-env seed = env id, uniform random actions); 4 of them to truncation
     "c2_random_500_n20": dict(grid=(500, 500), n=20, policy="random", steps=320, seeds=list(range(24))),
     "c2_random_500_n20_full": dict(grid=(500, 500), n=20, policy="random", steps=None, seeds=[0, 1, 2, 3]),

@@ -591,6 +591,88 @@ def nearest_sensor_greedy(env: "OracleEnv", probe):
     return 4, probes
 
 
+def _move_toward(env: "OracleEnv", tgt):
+    """GreedyAgent._move_toward (greedy_agents.py:41-68) toward sensor index `tgt`."""
+    ux, uy = env.pos[0], env.pos[1]                         # float32
+    dx, dy = env.spos[tgt, 0] - ux, env.spos[tgt, 1] - uy   # :43-45
+    if abs(dx) <= 0.5 and abs(dy) <= 0.5:
+        return 4
+    if abs(dx) > abs(dy):
+        nx, ny = ux + (1 if dx > 0 else -1), uy
+    else:
+        nx, ny = ux, uy + (1 if dy > 0 else -1)
+    if nx < 0 or nx >= env.W or ny < 0 or ny >= env.H:      # :57-59
+        return 4
+    mx, my = nx - ux, ny - uy
+    if mx > 0:
+        return 3
+    if mx < 0:
+        return 2
+    if my > 0:
+        return 0
+    if my < 0:
+        return 1
+    return 4
+
+
+def max_throughput_greedy_v2(env: "OracleEnv", probe):
+    """Restatement of MaxThroughputGreedyV2.select_action (greedy_agents.py:105-200).
+    `probe(i)` returns the shadowing draw of `sensor_i.is_in_range`: the list comprehension at :133-138 probes
+    EVERY sensor with data (no early exit), in index order.  Returns (action, probes).
+
+    Arithmetic types follow the reference (numpy 2 promotion rules):
+      * distance is a float32 norm; `distance / grid_size[0] * 5.0 * dist_w` stays float32 (:174);
+      * `sensor.data_buffer` is np.float64 until the sensor first overflows -- iot_sensors.py:120 then assigns the
+        Python float `max_buffer_size`, and every later value derives from it -- so for a sensor that has ever
+        lost data `sf_score + buffer_score + duty_score` is a Python float and subtracting the np.float32 penalty
+        rounds the whole score to float32 (weak-scalar promotion); otherwise the score is float64 (:176)."""
+    thr = env.p["rssi_threshold"]
+    probes = np.full(env.n, np.nan)
+    det = env._det()
+    battery_pct = env.battery / 274.0                       # :126 (hard-coded capacity)
+    max_steps = env.p["max_steps"]
+    steps_left = max_steps - env.step_count                 # :127
+    steps_ratio = min(1.0, steps_left / max_steps)          # :190
+    if battery_pct > 0.5 and steps_ratio > 0.5:             # :192-197
+        sf_thr = 9
+    elif battery_pct > 0.2 and steps_ratio > 0.2:
+        sf_thr = 10
+    else:
+        sf_thr = 12
+    immediate = False
+    for i in range(env.n):                                  # :133-138
+        if env.buf[i] > 0:
+            probes[i] = probe(i)
+            if float(det[i] + probes[i]) >= thr and int(env.sf[i]) <= sf_thr:
+                immediate = True
+    if immediate:
+        return 4, probes
+    if battery_pct < 0.1 or steps_left < 50:                # :157-162
+        sf_w, dist_w = 1.0, 1.0
+    elif battery_pct < 0.3 or steps_left < 150:
+        sf_w, dist_w = 2.0, 1.0
+    else:
+        sf_w, dist_w = 5.0, 1.0
+    best_score, best = -np.inf, None
+    duty_prob = env.p["duty_cycle"] / 100.0                 # iot_sensors.py:105-106
+    for i in range(env.n):                                  # :167-180
+        if env.buf[i] <= 0:
+            continue
+        distance = np.linalg.norm(env.spos[i] - env.pos)    # np.float32
+        sf_score = max(0, 13 - int(env.sf[i])) * 5.0 * sf_w
+        py_float_buffer = env.lost[i] > 0
+        buf = float(env.buf[i]) if py_float_buffer else np.float64(env.buf[i])
+        buffer_score = (buf / env.p["max_buffer_size"]) * 10.0
+        duty_score = duty_prob * 2.0
+        distance_penalty = (distance / env.W) * 5.0 * dist_w
+        score = sf_score + buffer_score + duty_score - distance_penalty
+        if score > best_score:
+            best_score, best = score, i
+    if best is None:
+        return 4, probes
+    return _move_toward(env, best), probes
+
+
 COLLECT_KEYS = ("bytes_collected", "was_new_sensor", "was_empty", "all_sensors_collected",
                 "battery_used", "collision_count", "data_loss", "urgency_reduced",
                 "sensor_urgency")

@@ -24,7 +24,7 @@ def one(spec):
     out = PKG_DIR / "variants"
     out.mkdir(exist_ok=True)
     obj = out / ("uavsim_f32_%s.o" % tag)
-    cmd = [B._nvcc(), *B.ARCH, *B.COMMON, "-Xptxas=-v", *flags, "-c", str(B.CSRC / "uavsim_f32.cu"), "-o", str(obj)]
+    cmd = [B._nvcc(), *B.ARCH, *B.COMMON, *B.UNITS["uavsim_f32.cu"], "-Xptxas=-v", *flags, "-c", str(B.CSRC / "uavsim_f32.cu"), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         return tag, "FAILED\n" + r.stdout + r.stderr

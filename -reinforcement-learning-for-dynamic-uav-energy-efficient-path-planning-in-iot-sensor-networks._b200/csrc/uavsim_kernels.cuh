@@ -246,8 +246,13 @@ __device__ __forceinline__ T sensor_sum(const T (&v)[SPL], int N, int lane, doub
     }
 }
 
+// LoRa tables indexed by SF - 7 (throughput build: one indexed constant load instead of a per-lane switch ladder)
+__device__ __constant__ float kDataRateF32[6] = {5470 / 8.0f, 3125 / 8.0f, 1760 / 8.0f, 980 / 8.0f, 440 / 8.0f, 250 / 8.0f};
+__device__ __constant__ float kRequiredSnrF32[6] = {-6.0f, -9.0f, -12.0f, -15.0f, -17.5f, -20.0f};
+
 template <typename Real>
 __device__ __forceinline__ Real data_rate_of(int sf) {  // iot_sensors.py:13-20
+    if constexpr (!std::is_same<Real, double>::value) return kDataRateF32[min(max(sf - 7, 0), 5)];
     switch (sf) {
         case 7: return Real(5470 / 8.0);
         case 8: return Real(3125 / 8.0);
@@ -259,6 +264,7 @@ __device__ __forceinline__ Real data_rate_of(int sf) {  // iot_sensors.py:13-20
 }
 template <typename Real>
 __device__ __forceinline__ Real required_snr_of(int sf) {  // iot_sensors.py:22-29 (:199-200 default)
+    if constexpr (!std::is_same<Real, double>::value) return kRequiredSnrF32[min(max(sf - 7, 0), 5)];
     switch (sf) {
         case 7: return Real(-6.0);
         case 8: return Real(-9.0);
@@ -315,18 +321,16 @@ __device__ __forceinline__ Real det_rssi(const Params<Real>& p, float ux, float 
 // IoTSensor.update_spreading_factor (iot_sensors.py:223-259).  "No threshold matched" keeps the SF.
 template <typename Real>
 __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Real& ema, int& sf) {
-    if (ema != ema)
-        ema = rssi;
-    else
-        ema = (p.lambda * rssi) + (p.one_minus_lambda * ema);
-    if (ema > Real(-60))
-        sf = 7;
-    else if (ema > Real(-70))
-        sf = 9;
-    else if (ema > Real(-78))
-        sf = 11;
-    else if (ema > Real(-85))
-        sf = 12;
+    // Straight-line selects, no per-lane branches: lanes of a warp hold different sensors and an if / else-if
+    // chain compiles to a divergent branch ladder (BSSY / BRA / BSYNC per update).
+    const Real blended = (p.lambda * rssi) + (p.one_minus_lambda * ema);
+    ema = (ema != ema) ? rssi : blended;  // NaN = None: the first sample initialises the average
+    // the reference takes the FIRST match of the descending ladder -60 / -70 / -78 / -85 (iot_sensors.py:252-255),
+    // which is the LAST assignment of the ascending one
+    sf = ema > Real(-85) ? 12 : sf;
+    sf = ema > Real(-78) ? 11 : sf;
+    sf = ema > Real(-70) ? 9 : sf;
+    sf = ema > Real(-60) ? 7 : sf;
 }
 
 // UAVEnvironment._calculate_urgency (uav_env.py:376-384)
@@ -337,7 +341,7 @@ __device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real
     if constexpr (std::is_same<Real, double>::value)
         lr = gen > 0.0 ? lost / gen : 0.0;
     else
-        lr = gen > 0.f ? lost * fast_rcp(gen) : 0.f;
+        lr = lost * fast_rcp(fmaxf(gen, 1e-30f));  // gen == 0 implies lost == 0: 0 * 1e30 = 0 without a select
     const Real u = util * (Real(1) + lr * Real(10));
     return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
 }
@@ -612,18 +616,17 @@ __device__ __forceinline__ void store_sensors(const Buffers& b, const Params<Rea
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
+        const uint32_t i = row + (uint32_t)j;
+        SensorState<Real> v;  // packed by every lane; only the stores are predicated
+        v.buf = s[k].buf;
+        v.tx = s[k].tx;
+        v.lost = s[k].lost;
+        if constexpr (kParity)
+            v.ema = s[k].ema;
+        else
+            v.ema = pack_sf(s[k].ema, s[k].sf);
         if (s[k].active) {
-            const uint32_t i = row + (uint32_t)j;
-            SensorState<Real> v;
-            v.buf = s[k].buf;
-            v.tx = s[k].tx;
-            v.lost = s[k].lost;
-            if constexpr (kParity) {
-                v.ema = s[k].ema;
-                b.ssf[i] = (uint8_t)s[k].sf;
-            } else {
-                v.ema = pack_sf(s[k].ema, s[k].sf);
-            }
+            if constexpr (kParity) b.ssf[i] = (uint8_t)s[k].sf;
             st[i] = v;
             // parity build accumulates total_data_generated; throughput build only rewrites it on reset
             if (kParity || write_static) gen[i] = s[k].gen;
@@ -681,7 +684,7 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
         const Real urg = urgency_of(p, s[k].buf, s[k].lost, generated_of(p, s[k], h.elapsed));
         adr_update(p, s[k].det + dd[k], s[k].ema, s[k].sf);
         const bool in_range = (s[k].det + de[k]) >= p.thr;
-        if (s[k].active) {
+        {   // features computed by every lane (no per-lane branch); only the stores are predicated
             float* o = out + 3 + FPS * j;
             float f[FPS];
             f[0] = (float)div_const(s[k].buf, p.maxbuf, p.inv_maxbuf);
@@ -718,9 +721,11 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
                 }
             }
             if (srow) {
+                if (s[k].active) {
 #pragma unroll
-                for (int q = 0; q < FPS; ++q) srow[3 + FPS * j + q] = f[q];
-            } else {
+                    for (int q = 0; q < FPS; ++q) srow[3 + FPS * j + q] = f[q];
+                }
+            } else if (s[k].active) {
 #pragma unroll
                 for (int q = 0; q < FPS; ++q) {
                     o[q] = f[q];
@@ -1515,16 +1520,12 @@ __device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& s
         s[k].attempt = false;
         s[k].det = Real(0);
         s[k].cur = Real(0);
-        SensorState<Real> v;
-        v.buf = v.tx = v.lost = Real(0);
-        v.ema = Real(CUDART_NAN);
-        float2 xy = make_float2(0.f, 0.f);
-        Real g = Real(0);
-        if (s[k].active) {
-            v = sb.st[j];
-            xy = sb.pos[j + pos_off];
-            g = sb.gen[j + gen_off];
-        }
+        // Unconditional loads (the stage has 32 * SPL slots): a lane without a sensor reads whatever an earlier
+        // environment left there and runs the same arithmetic on it -- every reduction, ballot and store is
+        // masked by `active`, so the values never escape.
+        const SensorState<Real> v = sb.st[j];
+        const float2 xy = sb.pos[j + pos_off];
+        const Real g = sb.gen[j + gen_off];
         float ema;
         int sf;
         unpack_sf(v.ema, ema, sf);
@@ -1723,9 +1724,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     }
 
     compute_det(p, ts.x[k], ts.y[k], s);  // the UAV has already moved (phase A)
-#ifndef UAVSIM_X_NOCOLLECT
     if (collect) collect_action<Real, REPLAY, SPL, LEAN>(p, b, ts, ws, k, e, s, step_loss, lane);
-#endif
 
     if (flags & kFlagTruncated) {  // reward_function.py:59-67 (counted only when the episode ends this step)
         int starved = 0;

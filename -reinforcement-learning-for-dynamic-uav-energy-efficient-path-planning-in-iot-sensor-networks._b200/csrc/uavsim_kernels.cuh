@@ -1187,21 +1187,33 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         bool a = false;
-        if (s[k].active && s[k].buf > Real(0)) {
-            s[k].cur = s[k].det + da[k];
-            adr_update(p, s[k].cur, s[k].ema, s[k].sf);
-            const Real rb = s[k].det + db[k];
-            Real plink;
-            if (rb < p.thr) {
-                plink = Real(0);
-            } else {
-                const Real x = (rb - p.noise_floor) - required_snr_of<Real>(s[k].sf);
-                if constexpr (kParity)
+        if constexpr (kParity) {
+            if (s[k].active && s[k].buf > Real(0)) {
+                s[k].cur = s[k].det + da[k];
+                adr_update(p, s[k].cur, s[k].ema, s[k].sf);
+                const Real rb = s[k].det + db[k];
+                Real plink;
+                if (rb < p.thr) {
+                    plink = Real(0);
+                } else {
+                    const Real x = (rb - p.noise_floor) - required_snr_of<Real>(s[k].sf);
                     plink = 1.0 / (1.0 + exp(-x));
-                else
-                    plink = __fdividef(1.0f, 1.0f + __expf(-x));
+                }
+                a = (plink * p.duty_frac) > du[k];
             }
-            a = (plink * p.duty_frac) > du[k];
+        } else {  // the same, straight-line: every lane computes, selects keep the state of lanes without data
+            const bool has = s[k].active && s[k].buf > 0.f;
+            const float cur = s[k].det + da[k];
+            float ema2 = s[k].ema;
+            int sf2 = s[k].sf;
+            adr_update(p, cur, ema2, sf2);
+            s[k].cur = cur;  // only read for attempting lanes
+            s[k].ema = has ? ema2 : s[k].ema;
+            s[k].sf = has ? sf2 : s[k].sf;
+            const float rb = s[k].det + db[k];
+            const float x = (rb - p.noise_floor) - required_snr_of<float>(sf2);
+            const float plink = rb < p.thr ? 0.f : __fdividef(1.0f, 1.0f + __expf(-x));
+            a = has && (plink * p.duty_frac) > du[k];
         }
         s[k].attempt = a;
         att[k] = __ballot_sync(kFull, a);

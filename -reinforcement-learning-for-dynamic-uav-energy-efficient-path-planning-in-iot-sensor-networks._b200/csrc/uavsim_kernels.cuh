@@ -323,7 +323,12 @@ template <typename Real>
 __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Real& ema, int& sf) {
     // Straight-line selects, no per-lane branches: lanes of a warp hold different sensors and an if / else-if
     // chain compiles to a divergent branch ladder (BSSY / BRA / BSYNC per update).
-    const Real blended = (p.lambda * rssi) + (p.one_minus_lambda * ema);
+    Real blended;
+    if constexpr (std::is_same<Real, double>::value)
+        blended = (p.lambda * rssi) + (p.one_minus_lambda * ema);  // reference order, no contraction (-fmad=false)
+    else
+        blended = fmaf(p.lambda, rssi, p.one_minus_lambda * ema);  // explicit: a*b + c*d has two contractions, and
+                                                                    // instantiations must agree bit for bit
     ema = (ema != ema) ? rssi : blended;  // NaN = None: the first sample initialises the average
     // the reference takes the FIRST match of the descending ladder -60 / -70 / -78 / -85 (iot_sensors.py:252-255),
     // which is the LAST assignment of the ascending one
@@ -365,8 +370,10 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, Real sigma, R
         const float r = sigma * fast_sqrt(-1.3862943611198906f * __log2f(u1));  // -2 ln u = -2 ln2 lg2 u
         float s, c;
         __sincosf(6.2831853071795865f * u2, &s, &c);
-        z0 = r * c;
-        z1 = r * s;
+        // __fmul_rn is never contracted: `det + z` stays an add in every instantiation (an FMA fused at one call
+        // site and not at another would make the LEAN and the diagnostic kernels differ in the last bit)
+        z0 = __fmul_rn(r, c);
+        z1 = __fmul_rn(r, s);
     }
 }
 

@@ -125,3 +125,44 @@ def test_shard_invariance_checksum_of_checksums(pkg):
     assert (whole[:, 1] == sum(p[:, 1] for p in parts)).all()
     np.testing.assert_allclose(whole[:, 0], sum(p[:, 0] for p in parts), rtol=1e-12)
     np.testing.assert_allclose(whole[:, 2], sum(p[:, 2] for p in parts), rtol=1e-12)
+
+
+@pytest.mark.parametrize("N,stack", [(20, 1), (50, 1), (50, 4), (33, 1)])
+def test_lean_instantiation_equals_the_diagnostic_one(pkg, N, stack):
+    """The benchmarked kernel is the LEAN instantiation (optional features compiled out); the instantiation with
+    parity diagnostics attached is the one the oracle-replay tests exercise.  Same seed, same actions: state,
+    observations, rewards and episode statistics must be bit-identical between the two, through in-kernel
+    restarts (short battery)."""
+    import torch
+    E, T = 4096 + 7, 260
+    kw = dict(grid_size=(300, 300), num_sensors=N, seed=31, max_battery=14.0, n_stack=stack, precision="f32",
+              rng="philox", uav_start_position=(140.0, 150.0))
+    lean = pkg.UAVVecEnv(E, **kw)
+    diag = pkg.UAVVecEnv(E, step_detail=True, **kw)          # step_detail bound => not LEAN
+    lean.reset_tensors()
+    diag.reset_tensors()
+    g = torch.Generator(device=lean.device)
+    g.manual_seed(5)
+    dones = 0
+    for t in range(T):
+        a = torch.randint(0, 5, (E,), dtype=torch.int32, device=lean.device, generator=g)
+        a = torch.where(torch.rand(E, device=lean.device, generator=g) < 0.35, torch.full_like(a, 4), a)
+        lean.step_tensors(a)
+        diag.step_tensors(a)
+        assert torch.equal(lean.reward, diag.reward), t
+        assert torch.equal(lean.done, diag.done), t
+        dones += int(lean.done.sum().item())
+        if t % 20 == 0 or t == T - 1:
+            assert torch.equal(lean.obs, diag.obs), t
+            sl, sd = lean.state(), diag.state()
+            for k in sl:
+                assert torch.equal(sl[k], sd[k]) or (sl[k].is_floating_point() and torch.equal(torch.nan_to_num(sl[k]), torch.nan_to_num(sd[k]))), (t, k)
+    assert dones > E // 2                                     # restarts happened inside the launches
+    # float64 atomics from different warps: the order of additions is not reproducible, the sums agree to rounding
+    assert torch.allclose(lean.stat_sums, diag.stat_sums, rtol=1e-12, atol=0.0)
+    assert lean.stat_sums[-1] == diag.stat_sums[-1] == dones
+    rl, rd = lean.records(), diag.records()
+    for k in rl.dtype.names:
+        assert (rl[k] == rd[k]).all() or np.array_equal(rl[k], rd[k], equal_nan=True), k
+    lean.close()
+    diag.close()

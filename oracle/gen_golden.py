@@ -292,11 +292,77 @@ def generate_relational(name):
     print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
 
 
+# --------------------------------------------------------------------------
+# Sim-to-real evaluation wrappers (sim_to_real_analysis.py:170-245): GPS noise on the observed position, systematic
+# wind drift, observation latency.  Chained episodes with DummyVecEnv-style resets; the wrappers' own draws are
+# stored next to the slot tables ("extra": [gps_x, gps_y] per step / reset, [angle] after a WindDriftEnv reset).
+# --------------------------------------------------------------------------
+S2R_SCENARIOS = {
+    "gps5_300_n12": dict(cls="GPSNoisyEnv", extra=dict(gps_sigma=5.0), grid=(300, 300), n=12, seed=31, steps=220,
+                         p_collect=0.35, kwargs=dict(max_steps=90, max_battery=274.0, uav_start_position=(140.0, 160.0))),
+    "wind1_200_n12": dict(cls="WindDriftEnv", extra=dict(wind_drift=1.0), grid=(200, 200), n=12, seed=32, steps=260,
+                          p_collect=0.3, kwargs=dict(max_steps=100, max_battery=274.0, uav_start_position=(90.0, 110.0))),
+    "wind2_120_n20": dict(cls="WindDriftEnv", extra=dict(wind_drift=2.0), grid=(120, 120), n=20, seed=33, steps=240,
+                          p_collect=0.4, kwargs=dict(max_steps=80, max_battery=274.0, uav_start_position=(5.0, 100.0))),
+    "lat2_200_n10": dict(cls="LatencyEnv", extra=dict(latency_steps=2), grid=(200, 200), n=10, seed=34, steps=150,
+                         p_collect=0.4, kwargs=dict(max_steps=60, max_battery=274.0, uav_start_position=(100.0, 100.0))),
+}
+S2R_STEP_KEYS = ("reward", "truncated", "pos", "battery", "sf", "visited", "obs", "buf", "tx", "lost", "ema", "draws",
+                 "extra", "total_reward")
+
+
+def generate_sim_to_real(name):
+    import random
+    sc = S2R_SCENARIOS[name]
+    H.load_reference()
+    H.REC.normalise = True
+    ns, npx = H.load_sim_to_real_envs()
+    random.seed(sc["seed"])
+    np.random.seed(sc["seed"])
+    layout = np.random.uniform([0, 0], list(sc["grid"]), (sc["n"], 2))      # what the constructor is about to draw
+    np.random.seed(sc["seed"])
+    kw = dict(grid_size=sc["grid"], num_sensors=sc["n"], path_loss_exponent=3.8, rssi_threshold=-85.0,
+              sensor_duty_cycle=10.0)
+    kw.update(sc["kwargs"])
+    env = ns[sc["cls"]]([tuple(float(v) for v in p) for p in layout.astype(np.float32)], **sc["extra"], **kw)
+    assert np.array_equal(np.array(env.sensor_positions, dtype=np.float32), layout.astype(np.float32))
+    rng = np.random.default_rng(sc["seed"])
+    blob, ep, steps, actions = {}, 0, [], []
+    first = H.s2r_traced_reset(env, npx, seed=sc["seed"])
+    for t in range(sc["steps"]):
+        a = 4 if rng.random() < sc["p_collect"] else int(rng.integers(0, 4))
+        st = H.s2r_traced_step(env, npx, a)
+        steps.append(st)
+        actions.append(a)
+        if st["truncated"] or t == sc["steps"] - 1:
+            S = H.stack_steps(steps)
+            for k in S2R_STEP_KEYS:
+                blob["e%d/%s" % (ep, k)] = S[k]
+            blob["e%d/actions" % ep] = np.array(actions, dtype=np.int8)
+            for k in ("obs", "draws", "fill", "sf", "ema", "buf", "extra", "pos"):
+                blob["e%d/reset_%s" % (ep, k)] = first[k]
+            ep, steps, actions = ep + 1, [], []
+            if st["truncated"]:
+                first = H.s2r_traced_reset(env, npx)       # DummyVecEnv: reset right after the terminal step
+    meta = dict(name=name, flavour="norm", cls=sc["cls"], extra=sc["extra"], grid=list(sc["grid"]), n=sc["n"],
+                start=list(sc["kwargs"]["uav_start_position"]), episodes=ep, env_kwargs=sc["kwargs"],
+                numpy=np.__version__, python=platform.python_version(), generator="oracle/gen_golden.py",
+                reference_entry="src/agents/dqn/dqn_evaluation_results/sim_to_real_analysis.py::%s (exec'd slice)" % sc["cls"])
+    blob["positions"] = layout.astype(np.float32)
+    blob["meta"] = np.array(json.dumps(meta))
+    path = OUT / ("%s.norm.npz" % name)
+    np.savez_compressed(path, **blob)
+    print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
+
+
 RAW_TOO = ("c1_greedy_500_n20",)
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS) + list(REL_SCENARIOS))
+    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS) + list(REL_SCENARIOS) + list(S2R_SCENARIOS))
     for nm in names:
+        if nm in S2R_SCENARIOS:
+            generate_sim_to_real(nm)
+            continue
         if nm in DR_SCENARIOS:
             generate_domain_rand(nm)
             continue

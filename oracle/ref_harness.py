@@ -499,3 +499,73 @@ def rel_traced_step(env, action):
     for k in ("ndr", "jains", "efficiency"):
         st["m_" + k] = np.float64(info.get(k, np.nan))
     return st
+
+
+# --------------------------------------------------------------------------
+# Sim-to-real evaluation wrappers (src/agents/dqn/dqn_evaluation_results/sim_to_real_analysis.py:128-245):
+# FixedLayoutEnv / PaddedFixedEnv / GPSNoisyEnv / WindDriftEnv / LatencyEnv
+# --------------------------------------------------------------------------
+class _ExtraNumpyProxy:
+    """`np` inside the exec'd slice: the wrappers' OWN draws (GPS noise, wind angle) come from the global legacy
+    stream like the reference's, and are also appended to `extra` so fixtures can carry them."""
+
+    class _Random:
+        def __init__(self, real, owner):
+            self._real, self._owner = real, owner
+
+        def normal(self, *a, **k):
+            v = self._real.normal(*a, **k)
+            self._owner.extra.append(float(v))
+            return v
+
+        def uniform(self, *a, **k):
+            v = self._real.uniform(*a, **k)
+            self._owner.extra.append(float(v))
+            return v
+
+        def __getattr__(self, name):
+            return getattr(self._real, name)
+
+    def __init__(self, real):
+        self._real = real
+        self.extra = []
+        self.random = self._Random(real.random, self)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+def load_sim_to_real_envs():
+    """Return (namespace with the wrapper classes, numpy proxy).  The module itself needs SB3, pandas, a trained
+    model and writes result directories at import; only the text of its ENVIRONMENT WRAPPERS section is exec'd,
+    unchanged, against the proxied reference env."""
+    mods = load_reference()
+    if "s2r_ns" in mods:
+        return mods["s2r_ns"], mods["s2r_np"]
+    load_greedy_agents()
+    path = REFERENCE_ROOT / "src" / "agents" / "dqn" / "dqn_evaluation_results" / "sim_to_real_analysis.py"
+    lines = path.read_text().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("class FixedLayoutEnv"))
+    stop = next(i for i, l in enumerate(lines) if "EPISODE RUNNERS" in l)
+    src = "\n" * start + "\n".join(lines[start:stop])          # keep the reference's line numbers in tracebacks
+    proxy = _ExtraNumpyProxy(np)
+    import gymnasium
+    ns = {"__name__": "sim_to_real_slice", "__file__": str(path), "np": proxy, "gymnasium": gymnasium,
+          "UAVEnvironment": mods["UAVEnvironment"], "MAX_SEN_LIMIT": 50}
+    exec(compile(src, str(path), "exec"), ns)
+    mods["s2r_ns"], mods["s2r_np"] = ns, proxy
+    return ns, proxy
+
+
+def s2r_traced_reset(env, npx, seed=None):
+    npx.extra.clear()
+    st = traced_reset(env, seed=seed)
+    st["extra"] = np.array(npx.extra + [np.nan] * (4 - len(npx.extra)), dtype=np.float64)
+    return st
+
+
+def s2r_traced_step(env, npx, action):
+    npx.extra.clear()
+    st = traced_step(env, action)
+    st["extra"] = np.array(npx.extra + [np.nan] * (4 - len(npx.extra)), dtype=np.float64)
+    return st

@@ -673,6 +673,72 @@ def max_throughput_greedy_v2(env: "OracleEnv", probe):
     return _move_toward(env, best), probes
 
 
+class SimToRealOracle:
+    """Restatement of the sim-to-real evaluation wrappers
+    (src/agents/dqn/dqn_evaluation_results/sim_to_real_analysis.py) over an OracleEnv:
+      PaddedFixedEnv :140-167  zero padding to `obs_slots` sensor slots
+      GPSNoisyEnv    :170-189  obs[0], obs[1] += N(0, gps_sigma) -- added to the NORMALISED entries, as executed
+      WindDriftEnv   :192-224  per-episode drift vector (angle ~ U(0, 2 pi) drawn after reset); after every step
+                               the true position moves by it, clipped to [0, W-1] x [0, H-1], and obs[0], obs[1]
+                               report the RAW drifted position (not normalised), as executed
+      LatencyEnv     :227-245  FIFO of `latency_steps` observations primed with copies of the reset observation
+    The reference keeps these in separate classes; one wrapper instance applies whichever is switched on (wind,
+    then GPS noise, then latency).  Their own draws come from the global legacy numpy stream; `extra` receives
+    them in call order ([gps_x, gps_y] per step / reset, [angle] after a wind reset).  `source(kind, a, b)` may be
+    given to replay recorded values instead."""
+
+    def __init__(self, env: "OracleEnv", gps_sigma=0.0, wind_drift=0.0, latency_steps=0, obs_slots=50, source=None):
+        self.env, self.gps_sigma, self.wind_drift, self.latency = env, gps_sigma, wind_drift, int(latency_steps)
+        self.fps = 5 if env.p["include_sensor_positions"] else 3
+        self.pad = (obs_slots - env.n) * self.fps
+        self.source = source or (lambda kind, a, b: getattr(np.random, kind)(a, b))
+        self.dx = self.dy = 0.0
+        self.extra = []
+        self.fifo = []
+
+    def _draw(self, kind, a, b):
+        v = self.source(kind, a, b)
+        self.extra.append(float(v))
+        return v
+
+    def _pad(self, raw):
+        return np.concatenate([raw, np.zeros(self.pad, dtype=np.float32)]).astype(np.float32)
+
+    def _gps(self, obs):
+        if self.gps_sigma > 0:                              # :176-181
+            obs = obs.copy()
+            obs[0] += self._draw("normal", 0, self.gps_sigma)
+            obs[1] += self._draw("normal", 0, self.gps_sigma)
+        return obs
+
+    def reset(self, fill):
+        self.extra = []
+        obs = self._gps(self._pad(self.env.reset(fill)))
+        if self.wind_drift > 0:                             # :205-210
+            angle = self._draw("uniform", 0, 2 * np.pi)
+            self.dx = self.wind_drift * np.cos(angle)
+            self.dy = self.wind_drift * np.sin(angle)
+        self.fifo = [obs.copy() for _ in range(self.latency)]   # :235-238
+        return obs
+
+    def step(self, action):
+        self.extra = []
+        env = self.env
+        obs, reward, terminated, truncated = env.step(action)
+        obs = self._pad(obs)
+        if self.wind_drift > 0:                             # :212-224
+            env.pos[0] = float(np.clip(env.pos[0] + self.dx, 0, env.W - 1))
+            env.pos[1] = float(np.clip(env.pos[1] + self.dy, 0, env.H - 1))
+            obs = obs.copy()
+            obs[0] = env.pos[0]
+            obs[1] = env.pos[1]
+        obs = self._gps(obs)
+        if self.latency:                                    # :240-245
+            self.fifo.append(obs.copy())
+            obs = self.fifo.pop(0)
+        return obs, reward, terminated, truncated
+
+
 COLLECT_KEYS = ("bytes_collected", "was_new_sensor", "was_empty", "all_sensors_collected",
                 "battery_used", "collision_count", "data_loss", "urgency_reduced",
                 "sensor_urgency")

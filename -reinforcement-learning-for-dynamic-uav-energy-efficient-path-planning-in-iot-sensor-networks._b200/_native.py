@@ -63,6 +63,7 @@ class Config(C.Structure):
         ("min_start_dist", _d), ("max_start_tries", _i32), ("reserved1", _i32), ("prox_eta", _d), ("jain_bonus", _d),
         ("rel_gamma", _d), ("rel_dwell_bonus", _d), ("rel_reward_scale", _d), ("rel_dwell_steps", _i32),
         ("rel_min_cluster", _i32),
+        ("gps_sigma", _d), ("wind_drift", _d),
     ]
 
 
@@ -84,7 +85,8 @@ class Scenario(C.Structure):
 
 class Replay(C.Structure):
     _fields_ = [("step_draws", C.c_void_p), ("reset_draws", C.c_void_p), ("reset_fill", C.c_void_p),
-                ("reset_init_sf", C.c_void_p), ("reset_scenario", Scenario), ("dwell_draws", C.c_void_p)]
+                ("reset_init_sf", C.c_void_p), ("reset_scenario", Scenario), ("dwell_draws", C.c_void_p),
+                ("step_env_draws", C.c_void_p), ("reset_env_draws", C.c_void_p)]
 
 
 class FieldView(C.Structure):
@@ -101,7 +103,7 @@ class EnvRecord(C.Structure):
                 ("visited_lo", C.c_uint32), ("visited_hi", C.c_uint32), ("capture_triggers", _i32),
                 ("boundary_hits", _i32), ("edge_steps", _i32), ("collisions", _i32),
                 ("first_full_coverage_step", _i32), ("episode", C.c_uint32), ("delivered", _i32),
-                ("init_sf", _i32), ("dwell_steps", _i32), ("reserved", _i32 * 2)]
+                ("init_sf", _i32), ("dwell_steps", _i32), ("wind_angle", C.c_double)]
 
 
 assert C.sizeof(EnvRecord) == 128
@@ -114,7 +116,7 @@ ENV_RECORD_DTYPE = [
     ("grid_w", "<i4"), ("grid_h", "<i4"), ("num_sensors", "<i4"), ("visited_lo", "<u4"), ("visited_hi", "<u4"),
     ("capture_triggers", "<i4"), ("boundary_hits", "<i4"), ("edge_steps", "<i4"), ("collisions", "<i4"),
     ("first_full_coverage_step", "<i4"), ("episode", "<u4"), ("delivered", "<i4"), ("init_sf", "<i4"),
-    ("dwell_steps", "<i4"), ("reserved", "<i4", (2,)),
+    ("dwell_steps", "<i4"), ("wind_angle", "<f8"),
 ]
 
 # Every symbol include/uavsim.h declares (tests/test_abi.py checks the header against this list).

@@ -77,6 +77,7 @@ int validate(const uavsim_config* c) {
     if (!(c->max_battery > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "max_battery must be > 0");
     if (!(c->collection_duration > 0)) return fail(UAVSIM_ERR_INVALID_ARG, "collection_duration must be > 0");
     if (c->init_sf < 7 || c->init_sf > 12) return fail(UAVSIM_ERR_INVALID_ARG, "init_sf must be in [7, 12]");
+    if (!(c->gps_sigma >= 0.0) || !(c->wind_drift >= 0.0)) return fail(UAVSIM_ERR_INVALID_ARG, "gps_sigma / wind_drift must be >= 0");
     if (c->wrapper != UAVSIM_WRAP_NONE && c->wrapper != UAVSIM_WRAP_RELATIONAL)
         return fail(UAVSIM_ERR_INVALID_ARG, "wrapper must be UAVSIM_WRAP_NONE or UAVSIM_WRAP_RELATIONAL");
     if (c->wrapper == UAVSIM_WRAP_RELATIONAL) {
@@ -168,6 +169,8 @@ Params<Real> make_params(const uavsim_config& c) {
     p.rel_gamma = (Real)c.rel_gamma;
     p.rel_dwell_bonus = (Real)c.rel_dwell_bonus;
     p.rel_scale = (Real)c.rel_reward_scale;
+    p.gps_sigma = (Real)c.gps_sigma;
+    p.wind_drift = c.wind_drift;
     p.max_battery = c.max_battery;
     p.batt_floor = 0.02 * c.max_battery;                       // uav.py:224
     p.e_move = (c.power_move_w * 1) / 3600;                    // uav.py:177-178
@@ -332,6 +335,8 @@ int uavsim_default_config(uavsim_config* c) {
     c->rel_reward_scale = 1e-5;            // env_wrapper.py:62
     c->rel_dwell_steps = 10;               // env_wrapper.py:50
     c->rel_min_cluster = 2;                // env_wrapper.py:51
+    c->gps_sigma = 0.0;
+    c->wind_drift = 0.0;
     return UAVSIM_OK;
 }
 
@@ -548,6 +553,8 @@ int uavsim_set_replay(uavsim_handle* h, const uavsim_replay* rp) {
     b.rs_grid_wh = rp->reset_scenario.grid_wh;
     b.rs_start_xy = rp->reset_scenario.start_xy;
     b.dwell_draws = rp->dwell_draws;
+    b.step_env_draws = rp->step_env_draws;
+    b.reset_env_draws = rp->reset_env_draws;
     return UAVSIM_OK;
 }
 

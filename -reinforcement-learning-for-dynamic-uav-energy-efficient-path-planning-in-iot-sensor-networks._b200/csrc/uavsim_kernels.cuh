@@ -75,6 +75,8 @@ struct Params {
     int32_t max_steps, init_sf, fps, obs_dim, obs_stride, P, domain_rand, auto_reset, num_grids, max_start_tries;
     int32_t relational, rel_dwell_steps, rel_min_cluster;  // RelationalUAVEnv wrapper (env_wrapper.py:47-62)
     Real rel_gamma, rel_dwell_bonus, rel_scale;
+    Real gps_sigma;     // GPSNoisyEnv (sim_to_real_analysis.py:170-189), 0 = off
+    double wind_drift;  // WindDriftEnv (:192-224), 0 = off
     int32_t frame_k, frame_mirror;  // VecFrameStack: k frames; offset (floats) of the mirrored copy, 0 when k == 1
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     uint32_t key0, key1;
@@ -108,6 +110,8 @@ struct Buffers {
     const int32_t* rs_grid_wh;
     const float* rs_start_xy;
     const double* dwell_draws;  // [E][P] relational wrapper's range probes (replay)
+    const double* step_env_draws;   // [E][4] sim-to-real wrappers, step: gps_x, gps_y (replay)
+    const double* reset_env_draws;  // [E][4] sim-to-real wrappers, reset: gps_x, gps_y, wind angle (replay)
     // bookkeeping
     double* stat_sums;
     unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
@@ -849,6 +853,28 @@ __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const
     }
 }
 
+// Per-environment draws of the sim-to-real wrappers (sim_to_real_analysis.py:176-181, :207): GPS noise pair for
+// the observation of `step` (0 = reset observation) and, at reset, the wind angle.  REPLAY: table [E][4];
+// PHILOX: stream kStreamMisc, counter word 3 = step << 8 | 4 (words 0, 1 there are the grid / inherited-SF draws).
+template <typename Real, bool REPLAY>
+__device__ __forceinline__ void env_draws(const Params<Real>& p, const double* table, int e, uint32_t episode, uint32_t step,
+                                          float& gx, float& gy, double& angle) {
+    if constexpr (REPLAY) {
+        gx = table ? (float)table[4 * (size_t)e + 0] : 0.f;  // obs[0] += python float: added as float32
+        gy = table ? (float)table[4 * (size_t)e + 1] : 0.f;
+        angle = table ? table[4 * (size_t)e + 2] : 0.0;
+    } else {
+        const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+        const Philox4 q = philox4x32_10((uint32_t)gid, ((uint32_t)(gid >> 32) & 0xffffffu) | (kStreamMisc << 24), episode,
+                                        (step << 8) | 4u, p.key0, p.key1);
+        Real z0, z1;
+        box_muller<Real>(q.x, q.y, p.gps_sigma, z0, z1);
+        gx = (float)z0;
+        gy = (float)z1;
+        angle = 6.283185307179586 * u01<double>(q.z);
+    }
+}
+
 // Start a new episode for this warp's environment: record in shared memory (ws.rec), sensors in
 // registers; writes the first observation.  FIXED: UAVEnvironment.reset (uav_env.py:400-427,
 // iot_sensors.py:305-321).  DOMAIN_RAND: DomainRandEnv.reset (dqn.py:301-372).  ws.rec.episode names
@@ -1026,6 +1052,19 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
         __syncwarp();
     }
     observe<Real, REPLAY, SPL, FPS, true, false>(p, h, s, dr, lane, out);
+    double wind_angle = 0.0;
+    if (p.gps_sigma > Real(0) || p.wind_drift > 0.0) {  // GPSNoisyEnv.reset :183-185, WindDriftEnv.reset :205-210
+        float gx, gy;
+        double angle;
+        env_draws<Real, REPLAY>(p, b.reset_env_draws, e, episode, 0u, gx, gy, angle);
+        __syncwarp();
+        if (lane == 0 && p.gps_sigma > Real(0)) {
+            out[0] = out[0] + gx;
+            out[1] = out[1] + gy;
+        }
+        wind_angle = angle;
+        __syncwarp();
+    }
     for (int i = 3 + FPS * N + lane; i < p.obs_dim; i += 32) out[i] = 0.0f;  // ghost slots
     if (p.frame_k > 1) {
         __syncwarp();
@@ -1056,6 +1095,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
         R.episode = episode + 1;
         R.init_sf = init_sf;
         R.dwell_steps = 0;
+        R.wind_angle = wind_angle;
         if (b.action_mask) b.action_mask[e] = action_mask_of(h.x, h.y, W, H);
     }
     __syncwarp();
@@ -1148,6 +1188,14 @@ __device__ __forceinline__ bool feat_domain_rand(const Params<Real>& p) {
 template <bool LEAN, typename Real>
 __device__ __forceinline__ bool feat_relational(const Params<Real>& p) {
     if constexpr (LEAN) return false; else return p.relational != 0;
+}
+template <bool LEAN, typename Real>
+__device__ __forceinline__ bool feat_gps(const Params<Real>& p) {
+    if constexpr (LEAN) return false; else return p.gps_sigma > Real(0);
+}
+template <bool LEAN, typename Real>
+__device__ __forceinline__ bool feat_wind(const Params<Real>& p) {
+    if constexpr (LEAN) return false; else return p.wind_drift > 0.0;
 }
 template <bool LEAN>
 __device__ __forceinline__ double* feat_step_detail(const Buffers& b) {
@@ -1636,11 +1684,11 @@ enum : int {
     kRX = 0, kRY = 1, kRStartX = 2, kRStartY = 3, kRBattery = 4, kRTotalReward = 6, kRTotalData = 8, kREpReturn = 10,
     kRLastBytes = 12, kRPrevDist = 13, kRElapsed = 14, kRStep = 15, kRGridW = 16, kRGridH = 17, kRN = 18, kRVisLo = 19,
     kRVisHi = 20, kRCapture = 21, kRBoundary = 22, kREdge = 23, kRCollisions = 24, kRFirstCov = 25, kREpisode = 26,
-    kRDelivered = 27, kRInitSf = 28, kRDwell = 29
+    kRDelivered = 27, kRInitSf = 28, kRDwell = 29, kRWindAngle = 30
 };
 static_assert(offsetof(uavsim_env_record, battery) == 4 * kRBattery && offsetof(uavsim_env_record, step) == 4 * kRStep &&
                   offsetof(uavsim_env_record, num_sensors) == 4 * kRN && offsetof(uavsim_env_record, episode) == 4 * kREpisode &&
-                  offsetof(uavsim_env_record, delivered) == 4 * kRDelivered && offsetof(uavsim_env_record, dwell_steps) == 4 * kRDwell && offsetof(uavsim_env_record, elapsed_s) == 4 * kRElapsed &&
+                  offsetof(uavsim_env_record, delivered) == 4 * kRDelivered && offsetof(uavsim_env_record, dwell_steps) == 4 * kRDwell && offsetof(uavsim_env_record, wind_angle) == 4 * kRWindAngle && offsetof(uavsim_env_record, elapsed_s) == 4 * kRElapsed &&
                   offsetof(uavsim_env_record, total_reward) == 4 * kRTotalReward && offsetof(uavsim_env_record, episode_return) == 4 * kREpReturn &&
                   offsetof(uavsim_env_record, prev_dist_nearest) == 4 * kRPrevDist && offsetof(uavsim_env_record, first_full_coverage_step) == 4 * kRFirstCov,
               "record word map out of date");
@@ -2104,7 +2152,19 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                     }
                 }
                 // commit the record (uav_env.py:487 and the counters of :300-307)
-                const float x = ts.x[lane], y = ts.y[lane];
+                float x = ts.x[lane], y = ts.y[lane];
+                if (feat_wind<LEAN>(p)) {  // WindDriftEnv.step, sim_to_real_analysis.py:214-219
+                    const double a = R.d(kRWindAngle);
+                    if constexpr (kParity) {  // np.float32 + np.float64 drift -> float64 sum, clip, one rounding to float32
+                        x = (float)fmin(fmax((double)x + p.wind_drift * cos(a), 0.0), (double)(R.i32(kRGridW) - 1));
+                        y = (float)fmin(fmax((double)y + p.wind_drift * sin(a), 0.0), (double)(R.i32(kRGridH) - 1));
+                    } else {
+                        float sn, cs;
+                        __sincosf((float)a, &sn, &cs);
+                        x = fminf(fmaxf(fmaf((float)p.wind_drift, cs, x), 0.f), (float)(R.i32(kRGridW) - 1));
+                        y = fminf(fmaxf(fmaf((float)p.wind_drift, sn, y), 0.f), (float)(R.i32(kRGridH) - 1));
+                    }
+                }
                 const double battery = ts.battery[lane];
                 R.set_f(kRX, x);
                 R.set_f(kRY, y);
@@ -2139,6 +2199,17 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                     f0 = __fdividef(x, (float)R.i32(kRGridW));
                     f1 = __fdividef(y, (float)R.i32(kRGridH));
                     f2 = (float)battery * p.inv_max_battery;
+                }
+                if (feat_wind<LEAN>(p)) {  // :220-223: the observation reports the raw drifted position
+                    f0 = x;
+                    f1 = y;
+                }
+                if (feat_gps<LEAN>(p)) {   // GPSNoisyEnv._add_gps_noise, :176-181
+                    float gx, gy;
+                    double unused;
+                    env_draws<Real, REPLAY>(p, b.step_env_draws, e, ts.episode[lane] - 1, (uint32_t)ts.step[lane], gx, gy, unused);
+                    f0 = f0 + gx;
+                    f1 = f1 + gy;
                 }
                 if constexpr (!kRowObs) {  // (the staged path wrote the whole row, head included, in phase B)
                     o[0] = f0;

@@ -62,7 +62,7 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
     const bool two = p.P > 32;
     // the plain UAVEnvironment step without optional features runs the LEAN instantiation (throughput build)
     const bool lean = !std::is_same<Real, double>::value && !replay && !p.domain_rand && !p.relational &&
-                      !b.draw_export && !b.step_detail && p.fps == 3
+                      !b.draw_export && !b.step_detail && p.fps == 3 && !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0)
 #ifdef UAVSIM_NO_LEAN
                       && false
 #endif

@@ -71,6 +71,7 @@ class UAVVecEnv:
                  # batched-simulator arguments
                  max_sensors: Optional[int] = None, obs_slots: Optional[int] = None, n_stack: int = 1,
                  domain_randomisation=False, curriculum_stage=0, relational=False,
+                 gps_sigma=0.0, wind_drift=0.0,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
                  device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
         if render_mode is not None:
@@ -126,6 +127,8 @@ class UAVVecEnv:
         cfg.reward_urgency_reduction = float(reward_urgency_reduction)
         cfg.penalty_battery = float(penalty_battery)
         cfg.reward_movement = float(reward_movement)
+        cfg.gps_sigma = float(gps_sigma)      # sim_to_real_analysis.py:170-189
+        cfg.wind_drift = float(wind_drift)    # sim_to_real_analysis.py:192-224
         self._stage = -1
         self.cfg = cfg
         self.domain_randomisation = bool(domain_randomisation)
@@ -253,7 +256,7 @@ class UAVVecEnv:
 
     def set_replay(self, step_draws=None, reset_draws=None, reset_fill=None, reset_init_sf=None,
                    reset_sensor_xy=None, reset_num_sensors=None, reset_grid_wh=None, reset_start_xy=None,
-                   dwell_draws=None):
+                   dwell_draws=None, step_env_draws=None, reset_env_draws=None):
         """Bind slot-addressed draw tables (device float64 tensors or numpy arrays); see
         include/uavsim.h `uavsim_replay`.  Arguments left None keep their previous binding."""
         dev = self.device
@@ -276,11 +279,15 @@ class UAVVecEnv:
         rs = up("rs_s", reset_start_xy, torch.float32)
         dw = up("dwell", dwell_draws, torch.float64)
         assert dw is None or tuple(dw.shape) == (E, P)
+        se = up("step_env", step_env_draws, torch.float64)
+        re_ = up("reset_env", reset_env_draws, torch.float64)
+        for t in (se, re_):
+            assert t is None or tuple(t.shape) == (E, 4), "per-env draw tables are [E, 4]"
         for t in (sd, rd):
             assert t is None or tuple(t.shape) == (E, N.NUM_SLOTS, P), "draw tables are [E, 6, P]"
         assert rf is None or tuple(rf.shape) == (E, P)
         rp = N.Replay(_ptr(sd), _ptr(rd), _ptr(rf), _ptr(ri), N.Scenario(_ptr(rxy), _ptr(rn), _ptr(rg), _ptr(rs)),
-                      _ptr(dw))
+                      _ptr(dw), _ptr(se), _ptr(re_))
         N.check(self.lib.uavsim_set_replay(self._h, C.byref(rp)))
 
     # ------------------------------------------------------------------ zero-copy tensor API

@@ -140,6 +140,12 @@ typedef struct uavsim_config {
     double rel_reward_scale;             /* 1e-5 */
     int32_t rel_dwell_steps;             /* 10 */
     int32_t rel_min_cluster;             /* 2 in-range sensors */
+
+    /* --- sim-to-real evaluation wrappers (dqn_evaluation_results/sim_to_real_analysis.py:170-224), 0 = off --- */
+    double gps_sigma;                    /* GPSNoisyEnv: obs[0], obs[1] += N(0, gps_sigma) every step and at reset (:176-181) */
+    double wind_drift;                   /* WindDriftEnv: per-episode drift vector of this length (angle ~ U(0, 2 pi) after
+                                            reset); after every step the true position moves by it, clipped to the grid, and
+                                            obs[0], obs[1] report the raw drifted position (:205-224) */
 } uavsim_config;
 
 /* State columns visible through uavsim_get_field (structure-of-arrays in HBM). */
@@ -176,7 +182,8 @@ typedef struct uavsim_env_record {
     int32_t delivered;          /* cumulative successful transmissions (iot_sensors.py:141-143) */
     int32_t init_sf;            /* SF the episode's sensors started with (12, or the inherited one of DomainRandEnv) */
     int32_t dwell_steps;        /* RelationalUAVEnv._dwell_steps */
-    int32_t reserved[2];
+    double wind_angle;          /* WindDriftEnv: direction of the running episode's drift vector (:207); the reference adds
+                                   wind_drift * cos / sin of it to the position in float64 */
 } uavsim_env_record;
 
 typedef struct uavsim_field_view {
@@ -259,6 +266,10 @@ typedef struct uavsim_replay {
     uavsim_scenario reset_scenario;
     const double* dwell_draws; /* [E][P]: shadowing values of the relational wrapper's is_in_range probes on a COLLECT step
                                   (env_wrapper.py:303), nullable unless wrapper == UAVSIM_WRAP_RELATIONAL */
+    const double* step_env_draws;  /* [E][4] per-env draws of the sim-to-real wrappers for the step about to run:
+                                      [0], [1] = GPS noise on obs[0], obs[1]; nullable unless gps_sigma > 0 */
+    const double* reset_env_draws; /* [E][4] the same for a reset: [0], [1] = GPS noise on the reset observation,
+                                      [2] = wind angle in [0, 2 pi); nullable unless gps_sigma > 0 or wind_drift > 0 */
 } uavsim_replay;
 
 typedef struct uavsim_handle uavsim_handle;

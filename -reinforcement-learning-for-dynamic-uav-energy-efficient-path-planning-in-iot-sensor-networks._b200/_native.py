@@ -63,7 +63,7 @@ class Config(C.Structure):
         ("min_start_dist", _d), ("max_start_tries", _i32), ("reserved1", _i32), ("prox_eta", _d), ("jain_bonus", _d),
         ("rel_gamma", _d), ("rel_dwell_bonus", _d), ("rel_reward_scale", _d), ("rel_dwell_steps", _i32),
         ("rel_min_cluster", _i32),
-        ("gps_sigma", _d), ("wind_drift", _d),
+        ("gps_sigma", _d), ("wind_drift", _d), ("latency_steps", _i32), ("reserved2", _i32),
     ]
 
 

@@ -38,6 +38,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr int64_t kAlign = 256;
+// frames kept per env: the stacked window plus the LatencyEnv delay line (sim_to_real_analysis.py:227-245)
+int ring_frames(const uavsim_config& c) { return c.frame_stack + c.latency_steps; }
+
 int64_t align_up(int64_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Layout {
@@ -59,6 +62,7 @@ int validate(const uavsim_config* c) {
     if (c->features_per_sensor != 3 && c->features_per_sensor != 5)
         return fail(UAVSIM_ERR_INVALID_ARG, "features_per_sensor must be 3 or 5 (uav_env.py:349)");
     if (c->frame_stack < 1 || c->frame_stack > 16) return fail(UAVSIM_ERR_INVALID_ARG, "frame_stack must be in [1, 16]");
+    if (c->latency_steps < 0 || c->latency_steps > 16) return fail(UAVSIM_ERR_INVALID_ARG, "latency_steps must be in [0, 16]");
     if (c->precision != UAVSIM_F64 && c->precision != UAVSIM_F32)
         return fail(UAVSIM_ERR_INVALID_ARG, "precision must be UAVSIM_F64 or UAVSIM_F32");
     if (c->rng_mode != UAVSIM_RNG_REPLAY && c->rng_mode != UAVSIM_RNG_PHILOX)
@@ -66,7 +70,7 @@ int validate(const uavsim_config* c) {
     if (c->reset_mode != UAVSIM_RESET_FIXED && c->reset_mode != UAVSIM_RESET_DOMAIN_RAND)
         return fail(UAVSIM_ERR_INVALID_ARG, "reset_mode must be UAVSIM_RESET_FIXED or UAVSIM_RESET_DOMAIN_RAND");
     if (c->grid_w <= 0 || c->grid_h <= 0) return fail(UAVSIM_ERR_INVALID_ARG, "grid must be positive");
-    if ((int64_t)c->num_envs * (3 + c->features_per_sensor * c->obs_slots) * (c->frame_stack > 1 ? 2 * c->frame_stack : 1) >= (1ll << 32))
+    if ((int64_t)c->num_envs * (3 + c->features_per_sensor * c->obs_slots) * (ring_frames(*c) > 1 ? 2 * ring_frames(*c) : 1) >= (1ll << 32))
         return fail(UAVSIM_ERR_INVALID_ARG, "num_envs * observation floats per env must be < 2^32 per handle");
     if ((int64_t)c->num_envs * c->max_sensors >= (1ll << 32))
         return fail(UAVSIM_ERR_INVALID_ARG, "num_envs * max_sensors must be < 2^32 per handle");
@@ -185,9 +189,11 @@ Params<Real> make_params(const uavsim_config& c) {
     p.init_sf = c.init_sf;
     p.fps = c.features_per_sensor;
     p.obs_dim = 3 + c.features_per_sensor * c.obs_slots;
-    p.frame_k = c.frame_stack;
-    p.frame_mirror = c.frame_stack > 1 ? c.frame_stack * p.obs_dim : 0;
-    p.obs_stride = p.obs_dim * (c.frame_stack > 1 ? 2 * c.frame_stack : 1);
+    p.frame_k = ring_frames(c);
+    p.frame_window = c.frame_stack;
+    p.latency = c.latency_steps;
+    p.frame_mirror = p.frame_k > 1 ? p.frame_k * p.obs_dim : 0;
+    p.obs_stride = p.obs_dim * (p.frame_k > 1 ? 2 * p.frame_k : 1);
     p.P = c.max_sensors;
     p.domain_rand = c.reset_mode == UAVSIM_RESET_DOMAIN_RAND;
     p.auto_reset = c.auto_reset != 0;
@@ -337,6 +343,8 @@ int uavsim_default_config(uavsim_config* c) {
     c->rel_min_cluster = 2;                // env_wrapper.py:51
     c->gps_sigma = 0.0;
     c->wind_drift = 0.0;
+    c->latency_steps = 0;
+    c->reserved2 = 0;
     return UAVSIM_OK;
 }
 
@@ -345,7 +353,7 @@ int uavsim_query_dims(const uavsim_config* c, uavsim_dims* out) {
     if (!out) return fail(UAVSIM_ERR_INVALID_ARG, "out is NULL");
     std::memset(out, 0, sizeof *out);
     out->obs_dim = 3 + c->features_per_sensor * c->obs_slots;
-    out->frame_rows = c->frame_stack > 1 ? 2 * c->frame_stack : 1;
+    out->frame_rows = ring_frames(*c) > 1 ? 2 * ring_frames(*c) : 1;
     out->obs_row_floats = out->obs_dim * out->frame_rows;
     out->real_bytes = real_bytes(c);
     out->arena_bytes = make_layout(c).total;
@@ -591,7 +599,7 @@ static int check_ready(uavsim_handle* h, bool reset) {
 int uavsim_reset(uavsim_handle* h, const uint8_t* mask, void* stream) {
     if (int rc = check_ready(h, true)) return rc;
     const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
-    const int k = h->cfg.frame_stack;
+    const int k = ring_frames(h->cfg);
     if (!mask || h->frame_slot < 0) h->frame_slot = k - 1;  // a full reset restarts the ring: window = k-1 zero frames + obs
     h->buf.frame_slot = h->frame_slot;
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_reset_f64(h->p64, h->buf, mask, replay, (cudaStream_t)stream)
@@ -607,7 +615,7 @@ int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
     const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
     if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
     h->buf.step_serial += 1;
-    h->frame_slot = (h->frame_slot + 1) % h->cfg.frame_stack;
+    h->frame_slot = (h->frame_slot + 1) % ring_frames(h->cfg);
     h->buf.frame_slot = h->frame_slot;
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_step_f64(h->p64, h->buf, actions, replay, (cudaStream_t)stream)
                                                    : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
@@ -653,7 +661,7 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
     if (int rc = uavsim_step(h, h->actions_dev, stream)) return rc;
     if (obs_host) {  // the stacked window [E][k*obs_dim] (a strided slice of the mirrored ring when k > 1)
         const size_t k = (size_t)h->cfg.frame_stack, od = (size_t)h->dims.obs_dim;
-        if (k == 1)
+        if (ring_frames(h->cfg) == 1)
             CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs, E * od * sizeof(float), cudaMemcpyDeviceToHost, st));
         else
             CUDA_TRY(cudaMemcpy2DAsync(obs_host, k * od * sizeof(float), h->buf.obs + (size_t)(h->frame_slot + 1) * od,

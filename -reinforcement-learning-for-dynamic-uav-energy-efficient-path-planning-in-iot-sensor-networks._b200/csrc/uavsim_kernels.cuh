@@ -77,7 +77,8 @@ struct Params {
     Real rel_gamma, rel_dwell_bonus, rel_scale;
     Real gps_sigma;     // GPSNoisyEnv (sim_to_real_analysis.py:170-189), 0 = off
     double wind_drift;  // WindDriftEnv (:192-224), 0 = off
-    int32_t frame_k, frame_mirror;  // VecFrameStack: k frames; offset (floats) of the mirrored copy, 0 when k == 1
+    int32_t frame_k, frame_mirror;  // frame ring: K = stack + latency frames; offset (floats) of the mirrored copy, 0 when K == 1
+    int32_t frame_window, latency;  // VecFrameStack window k (the OLDEST k frames of the ring); LatencyEnv delay
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     uint32_t key0, key1;
     PhiloxKeys keys;  // round-key schedule of (key0, key1)
@@ -1069,6 +1070,17 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     if (p.frame_k > 1) {
         __syncwarp();
         for (int i = lane; i < p.obs_dim; i += 32) out[i + p.frame_mirror] = out[i];
+        // LatencyEnv primes its FIFO with copies of the reset observation (sim_to_real_analysis.py:235-238): the
+        // `latency` frames behind the newest one hold the same row
+        float* blk = b.obs + (size_t)e * p.obs_stride;
+        for (int j = 1; j <= p.latency; ++j) {
+            const int r = (b.frame_slot - j + p.frame_k) % p.frame_k;
+            for (int i = lane; i < p.obs_dim; i += 32) {
+                const float v = out[i];
+                blk[r * p.obs_dim + i] = v;
+                blk[r * p.obs_dim + i + p.frame_mirror] = v;
+            }
+        }
     }
     const float prev = p.domain_rand ? nearest_with_data(h.x, h.y, s)
                                      : (p.relational ? nearest_unvisited(h.x, h.y, 0u, 0u, lane, s) : 0.f);
@@ -1616,7 +1628,7 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
     __syncwarp();
     const int N = ws.rec.num_sensors;
     if (b.terminal_obs) {  // the k stacked frames ending with the terminal one (written by this warp a moment ago)
-        const int total = p.frame_k * p.obs_dim;
+        const int total = p.frame_window * p.obs_dim;
         float* t = b.terminal_obs + (size_t)e * total;
         const float* win = b.obs + (size_t)e * p.obs_stride + (p.frame_k > 1 ? (b.frame_slot + 1) * p.obs_dim : 0);
         for (int i = lane; i < total; i += 32) t[i] = win[i];

@@ -71,7 +71,7 @@ class UAVVecEnv:
                  # batched-simulator arguments
                  max_sensors: Optional[int] = None, obs_slots: Optional[int] = None, n_stack: int = 1,
                  domain_randomisation=False, curriculum_stage=0, relational=False,
-                 gps_sigma=0.0, wind_drift=0.0,
+                 gps_sigma=0.0, wind_drift=0.0, latency_steps=0,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
                  device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
         if render_mode is not None:
@@ -129,6 +129,8 @@ class UAVVecEnv:
         cfg.reward_movement = float(reward_movement)
         cfg.gps_sigma = float(gps_sigma)      # sim_to_real_analysis.py:170-189
         cfg.wind_drift = float(wind_drift)    # sim_to_real_analysis.py:192-224
+        cfg.latency_steps = int(latency_steps)  # sim_to_real_analysis.py:227-245
+        self.latency_steps = int(latency_steps)
         self._stage = -1
         self.cfg = cfg
         self.domain_randomisation = bool(domain_randomisation)
@@ -203,7 +205,7 @@ class UAVVecEnv:
         """The current (stacked) observation [E, n_stack*obs_dim] as a zero-copy view of the bound buffer.
         With n_stack > 1 it is the window of the k newest frames, oldest first (VecFrameStack order), of the
         mirrored frame ring; the view moves every step, so fetch it again after each step."""
-        if self.n_stack == 1:
+        if self.n_stack + self.latency_steps == 1:
             return self._obs_buf
         s = int(self.lib.uavsim_frame_slot(self._h))
         od = self.dims.obs_dim

@@ -146,6 +146,11 @@ typedef struct uavsim_config {
     double wind_drift;                   /* WindDriftEnv: per-episode drift vector of this length (angle ~ U(0, 2 pi) after
                                             reset); after every step the true position moves by it, clipped to the grid, and
                                             obs[0], obs[1] report the raw drifted position (:205-224) */
+    int32_t latency_steps;               /* LatencyEnv: the observation handed out is the one from this many steps ago, the
+                                            FIFO primed with copies of the reset observation (:227-245).  On the device the
+                                            frame ring simply holds frame_stack + latency_steps frames and the stacked
+                                            window is its OLDEST frame_stack frames. */
+    int32_t reserved2;
 } uavsim_config;
 
 /* State columns visible through uavsim_get_field (structure-of-arrays in HBM). */
@@ -213,10 +218,11 @@ enum {
 /* Output buffers, allocated by the caller (e.g. torch tensors -> zero-copy), borrowed by the library.
  * reward dtype follows precision (float64 / float32).  Nullable members are optional. */
 typedef struct uavsim_outputs {
-    float* obs;            /* [E][frame_rows][obs_dim].  frame_stack == 1: one row.  frame_stack == k > 1: a mirrored ring
-                              of 2k rows; the step's frame goes to rows s and s+k (s = uavsim_frame_slot), so the k most
-                              recent frames, oldest first, are the contiguous rows s+1..s+k: the stacked observation of
-                              env e is the k*obs_dim floats at obs + e*frame_rows*obs_dim + (s+1)*obs_dim. */
+    float* obs;            /* [E][frame_rows][obs_dim].  K = frame_stack + latency_steps frames are kept.  K == 1: one row.
+                              K > 1: a mirrored ring of 2K rows; the step's frame goes to rows s and s+K
+                              (s = uavsim_frame_slot), so the K most recent frames, oldest first, are the contiguous rows
+                              s+1..s+K and the stacked observation of env e (the frame_stack oldest of them) is the
+                              frame_stack*obs_dim floats at obs + e*frame_rows*obs_dim + (s+1)*obs_dim. */
     void* reward;          /* [E] real */
     uint8_t* done;         /* [E] terminated|truncated (terminated is always false in the reference, uav_env.py:471) */
     float* terminal_obs;   /* [E][frame_stack*obs_dim] last (stacked) observation of a finished episode (auto_reset), nullable */
@@ -237,7 +243,7 @@ enum {
 typedef struct uavsim_dims {
     int32_t obs_dim;        /* 3 + features_per_sensor*obs_slots */
     int32_t obs_row_floats; /* floats per env in outputs.obs (= frame rows * obs_dim) */
-    int32_t frame_rows;     /* physical frame rows per env: 2k (mirrored ring) when frame_stack = k > 1, else 1 */
+    int32_t frame_rows;     /* physical frame rows per env: 2K (mirrored ring) when K = frame_stack + latency_steps > 1, else 1 */
     int32_t real_bytes;     /* 8 or 4 */
     int64_t arena_bytes;    /* device bytes uavsim_create needs for all state */
     int64_t replay_step_doubles;  /* doubles per env in a replay draw table: 6*P */

@@ -1,6 +1,6 @@
-"""Sim-to-real evaluation wrappers on the device (GPS noise on the observed position, systematic wind drift;
-sim_to_real_analysis.py:170-224): the CUDA parity build replays the sequences recorded from the reference's own
-GPSNoisyEnv / WindDriftEnv (tests/golden/gps*, wind*: chained episodes, one environment per recorded episode) and
+"""Sim-to-real evaluation wrappers on the device (GPS noise on the observed position, systematic wind drift,
+observation latency; sim_to_real_analysis.py:170-245): the CUDA parity build replays the sequences recorded from the reference's own
+GPSNoisyEnv / WindDriftEnv / LatencyEnv (tests/golden/gps*, wind*, lat*: chained episodes, one environment per recorded episode) and
 must reproduce observations bit for bit, positions and spreading factors exactly, rewards to 1e-9; the throughput
 build's Philox draws are checked statistically."""
 import json
@@ -20,7 +20,7 @@ def pkg():
     return import_package()
 
 
-@pytest.mark.parametrize("name", ["gps5_300_n12", "wind1_200_n12", "wind2_120_n20"])
+@pytest.mark.parametrize("name", ["gps5_300_n12", "wind1_200_n12", "wind2_120_n20", "lat2_200_n10"])
 def test_cuda_reproduces_reference_sim_to_real_sequences(pkg, name):
     import torch
     from golden_util import GOLDEN
@@ -103,3 +103,30 @@ def test_philox_gps_noise_and_wind_drift_statistics(pkg):
     rec = env.records()
     assert rec["x"].min() >= 0 and rec["x"].max() <= W - 1 and rec["y"].min() >= 0 and rec["y"].max() <= W - 1
     env.close()
+
+
+def test_latency_composes_with_frame_stacking(pkg):
+    """LatencyEnv under VecFrameStack (sim_to_real_analysis.py:246-250 wraps it that way): the stacked window must be
+    the k frames that END `latency` steps ago, primed with copies of the reset observation and zero frames before."""
+    import torch
+    E, n, k, L = 257, 8, 4, 3
+    kw = dict(grid_size=(200, 200), num_sensors=n, seed=12, uav_start_position=(100.0, 100.0), auto_reset=False)
+    plain = pkg.UAVVecEnv(E, **kw)
+    late = pkg.UAVVecEnv(E, n_stack=k, latency_steps=L, **kw)
+    od = plain.dims.obs_dim
+    frames = [plain.reset_tensors().clone()]
+    got = late.reset_tensors().clone()
+    g = torch.Generator(device=plain.device)
+    g.manual_seed(1)
+    for t in range(12):
+        # frame i of the delayed sequence: reset obs for i <= L, then the obs of step i - L; zero before the episode
+        seq = [frames[max(0, i - L)] if i >= 0 else torch.zeros_like(frames[0]) for i in range(t - k + 1, t + 1)]
+        assert torch.equal(got, torch.cat(seq, dim=1)), t
+        a = torch.randint(0, 5, (E,), dtype=torch.int32, device=plain.device, generator=g)
+        plain.step_tensors(a)
+        late.step_tensors(a)
+        frames.append(plain.obs.clone())
+        got = late.obs.clone()
+        assert got.shape == (E, k * od)
+    plain.close()
+    late.close()

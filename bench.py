@@ -335,7 +335,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bpe,
-                         "kernel": "uavsim::step_kernel<float,false,%d>" % (2 if n > 32 else 1),
+                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=true>" % (2 if n > 32 else 1),
                          "launch_ms": launch_ms},
             "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cpu_baseline_native": cpu_c,

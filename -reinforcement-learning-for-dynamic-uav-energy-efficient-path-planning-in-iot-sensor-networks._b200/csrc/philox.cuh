@@ -71,7 +71,8 @@ enum : uint32_t {
     kStreamFill = 1,    // initial buffer fill, uav_env.py:410
     kStreamLayout = 2,  // sensor layout, uav_env.py:366-374 / dqn.py:342-343
     kStreamStart = 3,   // far-start candidates, dqn.py:375-403
-    kStreamMisc = 4     // grid choice (dqn.py:283) and the inherited-SF draw (dqn.py:345-353)
+    kStreamMisc = 4,    // grid choice (dqn.py:283) and the inherited-SF draw (dqn.py:345-353)
+    kStreamPair = 6     // observation draws of a step shared by an even/odd environment pair (P <= 32; 5 = driver probes)
 };
 
 }  // namespace uavsim

@@ -62,6 +62,8 @@ int validate(const uavsim_config* c) {
     if (c->features_per_sensor != 3 && c->features_per_sensor != 5)
         return fail(UAVSIM_ERR_INVALID_ARG, "features_per_sensor must be 3 or 5 (uav_env.py:349)");
     if (c->frame_stack < 1 || c->frame_stack > 16) return fail(UAVSIM_ERR_INVALID_ARG, "frame_stack must be in [1, 16]");
+    if (c->rng_mode == UAVSIM_RNG_PHILOX && c->max_sensors <= 32 && (c->env_id_offset & 1))
+        return fail(UAVSIM_ERR_INVALID_ARG, "env_id_offset must be even when max_sensors <= 32 (observation draws are shared by even/odd environment pairs)");
     if (c->latency_steps < 0 || c->latency_steps > 16) return fail(UAVSIM_ERR_INVALID_ARG, "latency_steps must be in [0, 16]");
     if (c->precision != UAVSIM_F64 && c->precision != UAVSIM_F32)
         return fail(UAVSIM_ERR_INVALID_ARG, "precision must be UAVSIM_F64 or UAVSIM_F32");

@@ -407,10 +407,20 @@ struct Draws {
     const double* tab;  // replay table of this environment (REPLAY only)
     Real* exp;          // optional export of the draws actually used, [6][P]
     uint32_t env_lo, env_hi, episode, step;
+    // P <= 32 (one slot per lane): the D, E draws of a STEP come from ONE Philox call per environment PAIR
+    // (global ids 2m, 2m+1): counter = (m, kStreamPair | hi bits, episode and step of the EVEN environment,
+    // lane << 3); words (x, y) serve the even environment, (z, w) the odd one.  A call then feeds two sensors
+    // whatever the sensor count, and the pair kernel (two environments per warp pass) issues it once.
+    uint32_t pair_episode, pair_step;
+    bool paired;
 
     __device__ __forceinline__ Philox4 call(const Params<Real>& p, int lane, uint32_t c) const {
         return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c,
                              p.keys);
+    }
+    __device__ __forceinline__ Philox4 pair_call(const Params<Real>& p, int lane) const {
+        return philox4x32_10((env_lo >> 1) | (env_hi << 31), (env_hi >> 1) | (kStreamPair << 24), pair_episode,
+                             (pair_step << 8) | ((uint32_t)lane << 3), p.keys);
     }
     __device__ __forceinline__ void put(const Params<Real>& p, int slot, int j, Real v) const {
         if (exp && j < p.P) exp[slot * p.P + j] = v;
@@ -425,9 +435,15 @@ struct Draws {
                 e[k] = in ? (Real)tab[UAVSIM_SLOT_E * p.P + j] : Real(0);
             }
         } else {
-            const Philox4 q0 = call(p, lane, 0);
-            box_muller<Real>(q0.x, q0.y, p.sigma, d[0], e[0]);
-            if constexpr (SPL == 2) box_muller<Real>(q0.z, q0.w, p.sigma, d[1], e[1]);
+            if constexpr (SPL == 2) {
+                const Philox4 q0 = call(p, lane, 0);
+                box_muller<Real>(q0.x, q0.y, p.sigma, d[0], e[0]);
+                box_muller<Real>(q0.z, q0.w, p.sigma, d[1], e[1]);
+            } else {
+                const Philox4 q0 = paired ? pair_call(p, lane) : call(p, lane, 0);
+                const bool odd = paired && (env_lo & 1u);
+                box_muller<Real>(odd ? q0.z : q0.x, odd ? q0.w : q0.y, p.sigma, d[0], e[0]);
+            }
             if (exp) {
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) {
@@ -1044,6 +1060,8 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     dr.env_hi = env_hi;
     dr.episode = episode;
     dr.step = 0;
+    dr.paired = false;  // a reset observation belongs to one environment: (env, episode, step 0)
+    dr.pair_episode = dr.pair_step = 0;
     dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = exp;
     float* out = obs_frame(p, b, e);
@@ -1729,6 +1747,11 @@ __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real
     dr.env_hi = (uint32_t)(gid >> 32) & 0xffffffu;
     dr.episode = ts.episode[k] - 1;  // the record counts resets done; the running episode is one less
     dr.step = (uint32_t)ts.step[k];
+    // pair time = the even environment of the pair (tiles start at multiples of 16 and env_id_offset is even when
+    // P <= 32, so it is slot k & ~1 of this tile; phase A publishes episode / step of every slot, valid or not)
+    dr.paired = SPL == 1;
+    dr.pair_episode = ts.episode[k & ~1] - 1;
+    dr.pair_step = (uint32_t)ts.step[k & ~1];
     dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = (!REPLAY && feat_draw_export<LEAN>(b))
                  ? reinterpret_cast<Real*>(feat_draw_export<LEAN>(b)) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
@@ -1954,6 +1977,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
             const int e = base + lane;
             int my_flags = 0;
             const int my_action = ts.action[tb][lane];
+            ts.step[lane] = R.i32(kRStep) + 1;     // published for every slot: the even slot is its pair's clock
+            ts.episode[lane] = R.w(kREpisode);
             if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
                 atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
             } else {
@@ -2003,8 +2028,6 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
                 ts.y[lane] = y;
                 ts.elapsed[lane] = R.f(kRElapsed) + (float)(collect ? p.cd : Real(1));
                 ts.N[lane] = R.i32(kRN);
-                ts.step[lane] = step;
-                ts.episode[lane] = R.w(kREpisode);
                 ts.vis_lo[lane] = R.w(kRVisLo);
                 ts.vis_hi[lane] = R.w(kRVisHi);
                 ts.battery[lane] = battery;

@@ -63,6 +63,13 @@ def test_exported_draws_match_independent_philox(pkg, N):
         q0 = call(0)
         d0, e0 = box_muller(q0[0], q0[1], 4.0)
         if N <= 32:
+            # D, E of a step: one call per environment PAIR (stream 6), clocked by the even environment's episode /
+            # step; words (x, y) -> even environment, (z, w) -> odd environment
+            pair = np.broadcast_to(envs >> np.uint64(1), (E, 32))
+            c3 = (np.uint64(t) << np.uint64(8)) | (lanes[None, :] << np.uint64(3))
+            qp = philox4x32_10(pair, np.full((E, 32), 6 << 24, dtype=np.uint64), episode, np.broadcast_to(c3, (E, 32)), k0, k1)
+            odd = (envs & np.uint64(1)).astype(bool)
+            d0, e0 = box_muller(np.where(odd, qp[2], qp[0]), np.where(odd, qp[3], qp[1]), 4.0)
             np.testing.assert_allclose(exp[:, 4, :], d0[:, :N], rtol=1e-12, atol=1e-12)
             np.testing.assert_allclose(exp[:, 5, :], e0[:, :N], rtol=1e-12, atol=1e-12)
             if a == 4:

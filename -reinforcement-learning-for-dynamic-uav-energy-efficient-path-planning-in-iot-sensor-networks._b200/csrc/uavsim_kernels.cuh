@@ -679,6 +679,11 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 // into the row (the partial sectors of neighbouring lanes merge in L2; DRAM sees the row once); ghost
 // slots are zero-filled when the buffer is bound / an episode starts and never touched by a step (N is
 // fixed during an episode).
+template <typename Real, int SPL, int FPS, bool HEAD, bool MIRROR>
+__device__ __forceinline__ void observe_with(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
+                                             const Real (&dd)[SPL], const Real (&de)[SPL], int lane,
+                                             float* __restrict__ out, float* srow);
+
 // srow != nullptr (staged step path): the features go to a row image in shared memory instead, and the caller
 // writes the row to HBM with consecutive lanes on consecutive floats (store_obs_row) -- a lane-per-sensor store
 // with a stride of FPS floats touches 12 sectors per instruction and leaves the merging to L1/L2.
@@ -686,10 +691,19 @@ template <typename Real, bool REPLAY, int SPL, int FPS, bool HEAD, bool MIRROR>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
                                         const Draws<Real, REPLAY, SPL>& dr, int lane, float* __restrict__ out,
                                         float* srow = nullptr) {
-    constexpr bool kParity = std::is_same<Real, double>::value;
-    const int mirror = MIRROR ? p.frame_mirror : 0;
     Real dd[SPL], de[SPL];
     dr.obs(p, lane, dd, de);
+    observe_with<Real, SPL, FPS, HEAD, MIRROR>(p, h, s, dd, de, lane, out, srow);
+}
+
+// The observation pass with the D / E draws already in hand (the pair kernel makes one Philox call for two
+// environments and runs this once per environment).
+template <typename Real, int SPL, int FPS, bool HEAD, bool MIRROR>
+__device__ __forceinline__ void observe_with(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
+                                             const Real (&dd)[SPL], const Real (&de)[SPL], int lane,
+                                             float* __restrict__ out, float* srow) {
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    const int mirror = MIRROR ? p.frame_mirror : 0;
     float inv_w = 0.f, inv_h = 0.f;
     if constexpr (!kParity && FPS == 5) {
         inv_w = fast_rcp((float)h.W);
@@ -1152,13 +1166,13 @@ constexpr int min_blocks_per_sm() {
 #ifndef UAVSIM_B1
 #define UAVSIM_B1 3
 #endif
-template <typename Real, int SPL>
+template <typename Real, int SPL, bool PAIR = false>
 __host__ __device__ constexpr int step_warps() {
-    return std::is_same<Real, double>::value ? 8 : (SPL == 2 ? UAVSIM_W2 : UAVSIM_W1);
+    return std::is_same<Real, double>::value ? 8 : ((SPL == 2 || PAIR) ? UAVSIM_W2 : UAVSIM_W1);
 }
-template <typename Real, int SPL>
+template <typename Real, int SPL, bool PAIR = false>
 __host__ __device__ constexpr int step_min_blocks() {
-    return std::is_same<Real, double>::value ? 1 : (SPL == 2 ? UAVSIM_B2 : UAVSIM_B1);
+    return std::is_same<Real, double>::value ? 1 : ((SPL == 2 || PAIR) ? UAVSIM_B2 : UAVSIM_B1);
 }
 
 template <typename Real, bool REPLAY, int SPL, int FPS>
@@ -1693,16 +1707,16 @@ struct alignas(16) TileSmem {
 
 // Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
 // the tile block and (float32 layout) two stage buffers.
-template <typename Real, int SPL>
+template <typename Real, int SPL, bool PAIR = false>
 struct alignas(alignof(SensorState<Real>) > 16 ? alignof(SensorState<Real>) : 16) StepWarpSmem {
     WarpSmem ws;
     TileSmem<Real> ts;
-    StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : 2];
+    StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : (PAIR ? 4 : 2)];  // pair kernel: 2 stages x 2 envs
     uint64_t bar[2];  // one mbarrier per stage (bulk-copy pipeline)
 };
-template <typename Real, int SPL>
+template <typename Real, int SPL, bool PAIR = false>
 constexpr size_t step_smem_bytes() {
-    return sizeof(StepWarpSmem<Real, SPL>) * step_warps<Real, SPL>();
+    return sizeof(StepWarpSmem<Real, SPL, PAIR>) * step_warps<Real, SPL, PAIR>();
 }
 
 enum : int {
@@ -1913,17 +1927,108 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
     store_sensors<Real, SPL>(b, p, e, lane, s, false);
 }
 
+// ------------------------------------------------------------------------------------------------
+// P <= 32, plain environment (LEAN): TWO environments per warp pass.  With one sensor slot per lane a pass over
+// one environment leaves 12 of 32 lanes idle at N = 20 and uses half of each Philox call; here slot q of a lane
+// is sensor `lane` of environment k0 + q, so the per-sensor arithmetic of the two environments interleaves like
+// the two slots of the P > 32 kernel, the observation draws of both come from ONE Philox call (the pair-keyed
+// counter of Draws), and the per-pass loop control is paid once per pair.  Everything per environment -- collect
+// action, reductions, stores -- runs the one-slot building blocks on a one-element view of s[q].
+// ------------------------------------------------------------------------------------------------
+template <bool STACK>
+__device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers& b, TileSmem<float>& ts, WarpSmem& ws,
+                                           int k0, int base, int lane, const StageBuf<float, 1>* st2, bool have_b) {
+    using View = Sensor<float>(&)[1];
+    Sensor<float> s[2];
+    int flags[2], N[2];
+    bool valid[2], collect[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int k = k0 + q;
+        flags[q] = (q == 0 || have_b) ? ts.flags[k] : 0;
+        valid[q] = flags[q] & kFlagValid;
+        collect[q] = flags[q] & kFlagCollect;
+        N[q] = valid[q] ? ts.N[k] : 0;  // an absent / rejected environment has no active lane: nothing is reduced or stored
+        const uint32_t row = (uint32_t)(base + k) * (uint32_t)p.P;
+        load_sensors_staged<float, 1>(st2[q], N[q], lane, reinterpret_cast<View>(s[q]), (int)(row & 1u), (int)(row & 3u));
+    }
+    __syncwarp();
+    if (!(valid[0] || valid[1])) return;
+
+    // ---- iot_sensors.py:114-125: age the buffers ----
+    float step_loss[2];
+    {
+        float loss[2];
+        bool any_over[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float nw = p.rate * (collect[q] ? p.cd : 1.0f);
+            const float pot = s[q].buf + nw;
+            const bool over = pot > p.maxbuf;
+            loss[q] = over ? pot - p.maxbuf : 0.f;
+            s[q].buf = over ? p.maxbuf : pot;
+            s[q].lost += loss[q];
+            any_over[q] = s[q].active && over;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            step_loss[q] = 0.f;
+            if (__any_sync(kFull, any_over[q])) step_loss[q] = warp_sum(s[q].active ? loss[q] : 0.f);
+            if (lane == 0 && valid[q]) ts.step_loss[k0 + q] = step_loss[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) s[q].det = det_rssi(p, ts.x[k0 + q], ts.y[k0 + q], s[q].sx, s[q].sy);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        if (valid[q] && collect[q])
+            collect_action<float, false, 1, true>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
+                                                  step_loss[q], lane);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (flags[q] & kFlagTruncated) {  // reward_function.py:59-67
+            const float g = generated_of(p, s[q], ts.elapsed[k0 + q]);
+            const int starved = __popc(__ballot_sync(kFull, s[q].active && g > 0.f && fdiv(s[q].tx, g) < p.cr_thr));
+            if (lane == 0) ts.counts[k0 + q] |= starved << 16;
+        }
+    }
+    // ---- observation, sensor part: one Philox call for the pair (uav_env.py:638-674) ----
+    {
+        const Draws<float, false, 1> dr = step_draws<float, false, 1, true>(p, b, ts, k0, base + k0);
+        const Philox4 qp = dr.pair_call(p, lane);
+        float dd[2][1], de[2][1];
+        box_muller<float>(qp.x, qp.y, p.sigma, dd[0][0], de[0][0]);
+        box_muller<float>(qp.z, qp.w, p.sigma, dd[1][0], de[1][0]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            Hot h;
+            h.x = h.y = 0.f;
+            h.elapsed = ts.elapsed[k0 + q];
+            h.W = h.H = 1;
+            h.N = N[q];
+            h.battery = 0.0;
+            h.vis_lo = h.vis_hi = 0u;
+            observe_with<float, 1, 3, false, STACK>(p, h, reinterpret_cast<View>(s[q]), dd[q], de[q], lane,
+                                                    obs_frame(p, b, base + k0 + q), nullptr);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) store_sensors<float, 1>(b, p, base + k0 + q, lane, reinterpret_cast<View>(s[q]), false);
+}
+
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN = false>
-__global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<Real, SPL>())
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN = false, bool PAIR = false>
+__global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_blocks<Real, SPL, PAIR>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    StepWarpSmem<Real, SPL>& mine = reinterpret_cast<StepWarpSmem<Real, SPL>*>(dyn_smem)[warp];
+    static_assert(!PAIR || (LEAN && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
+                  "the pair kernel is the plain throughput step with one sensor slot per lane");
+    StepWarpSmem<Real, SPL, PAIR>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR>*>(dyn_smem)[warp];
     WarpSmem& ws = mine.ws;
     TileSmem<Real>& ts = mine.ts;
     StageBuf<Real, SPL>* stage = mine.stage;
@@ -1931,8 +2036,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
     // carried in registers: with 184 KB of the SM given to shared memory the L1 is small and a spilled
     // loop-carried value costs an L2 round trip per environment
 #define UAVSIM_E (b.E)
-#define UAVSIM_TILE_STRIDE ((int)gridDim.x * step_warps<Real, SPL>() * kTile)
-    int base = (blockIdx.x * step_warps<Real, SPL>() + warp) * kTile;
+#define UAVSIM_TILE_STRIDE ((int)gridDim.x * step_warps<Real, SPL, PAIR>() * kTile)
+    int base = (blockIdx.x * step_warps<Real, SPL, PAIR>() + warp) * kTile;
     int tb = 0;  // tile buffer in use
     constexpr bool kBulk = kStaged && (UAVSIM_BULK_STAGE != 0);  // sensor columns by bulk copy + mbarrier
     constexpr bool kRowObs = kStaged && (UAVSIM_ROW_OBS != 0);   // observation row staged in smem, coalesced store
@@ -1951,11 +2056,16 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
             }
         } else if (base < UAVSIM_E) {
             tile_issue<Real>(b, actions, base, 0, lane, ts);
-            stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
+            if constexpr (!PAIR) stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
         }
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
+        if constexpr (PAIR) {  // the first pair of the warp's sequence (sensor counts from the records just landed)
+            if (base < UAVSIM_E) stage_issue<Real, SPL>(b, p, base, (int)ts.rec[0][0][kRN], lane, stage[0]);
+            if (base + 1 < UAVSIM_E) stage_issue<Real, SPL>(b, p, base + 1, (int)ts.rec[0][1][kRN ^ 1], lane, stage[1]);
+            cp_async_commit();
+        }
     }
 
     for (; base < UAVSIM_E; base += UAVSIM_TILE_STRIDE) {
@@ -2038,8 +2148,51 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL>(), step_min_blocks<
         }
         __syncwarp();
 
+        // ---- phase B (pair kernel): two environments per warp pass ----
+        if constexpr (PAIR) {
+            // Stages: pair buffer pb holds the current pair (2 environments), pb ^ 1 receives the next pair.  cp.async
+            // groups in commit order: G(j) per pair iteration j, the next tile's records + actions T right after G(0);
+            // T is read from the last pair iteration on.
+            for (int k = 0; k < ntile; k += 2) {
+                const int pb = (k >> 1) & 1;
+                int e1 = base + k + 2, n1a = 0, n1b = 0;
+                bool ha = false, hb = false;
+                if (k + 2 < ntile) {
+                    n1a = (int)rec[k + 2][kRN ^ (k + 2)];
+                    ha = true;
+                    if (k + 3 < ntile) {
+                        n1b = (int)rec[k + 3][kRN ^ (k + 3)];
+                        hb = true;
+                    }
+                } else {
+                    e1 = base + UAVSIM_TILE_STRIDE;
+                    if (e1 < UAVSIM_E) {
+                        n1a = (int)ts.rec[tb ^ 1][0][kRN];
+                        ha = true;
+                        if (e1 + 1 < UAVSIM_E) {
+                            n1b = (int)ts.rec[tb ^ 1][1][kRN ^ 1];
+                            hb = true;
+                        }
+                    }
+                }
+                if (ha) stage_issue<Real, SPL>(b, p, e1, n1a, lane, stage[(pb ^ 1) * 2]);
+                if (hb) stage_issue<Real, SPL>(b, p, e1 + 1, n1b, lane, stage[(pb ^ 1) * 2 + 1]);
+                cp_async_commit();
+                if (k == 0) {
+                    if (base + UAVSIM_TILE_STRIDE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, base + UAVSIM_TILE_STRIDE, tb ^ 1, lane, ts);
+                    cp_async_commit();
+                }
+                if (k <= 2)
+                    cp_async_wait<2>();  // G(j) and T may still be in flight
+                else
+                    cp_async_wait<1>();  // only G(j): T has landed before the last iteration peeks at it
+                __syncwarp();
+                if constexpr (PAIR) pair_phase<STACK>(p, b, ts, ws, k, base, lane, &stage[pb * 2], k + 1 < ntile);
+            }
+        }
         // ---- phase B: one environment per warp, sensors across lanes ----
-        for (int k = 0; k < ntile; ++k) {
+        for (int k = 0; !PAIR && k < ntile; ++k) {
             const int e = base + k;
             Sensor<Real> s[SPL];
             if constexpr (kBulk) {

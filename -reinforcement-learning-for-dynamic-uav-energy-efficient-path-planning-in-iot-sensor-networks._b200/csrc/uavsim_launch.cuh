@@ -75,10 +75,10 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
                 constexpr int warps = step_warps<Real, 2>();
                 auto k = stack ? step_kernel<Real, false, 2, 3, true, true> : step_kernel<Real, false, 2, 3, false, true>;
                 k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
-            } else {
-                constexpr size_t smem = step_smem_bytes<Real, 1>();
-                constexpr int warps = step_warps<Real, 1>();
-                auto k = stack ? step_kernel<Real, false, 1, 3, true, true> : step_kernel<Real, false, 1, 3, false, true>;
+            } else {  // P <= 32: two environments per warp pass (uavsim_kernels.cuh, pair_phase)
+                constexpr size_t smem = step_smem_bytes<Real, 1, true>();
+                constexpr int warps = step_warps<Real, 1, true>();
+                auto k = stack ? step_kernel<Real, false, 1, 3, true, true, true> : step_kernel<Real, false, 1, 3, false, true, true>;
                 k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
             }
             return cudaGetLastError();

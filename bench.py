@@ -318,6 +318,30 @@ def run_gpu_arm(args):
         if not args.no_cpu:
             cpu = cpu_python_port(grid, n, envs_per_core=4, warm=5, steps=args.cpu_steps)
             cpu_c = cpu_c_port(grid, n, n_envs=8192, steps=20)
+        secondary = None
+        if not args.sensors and not args.no_secondary:
+            # the metric is quoted for N = 20-50: the same workload at N = 20 (pair kernel: two environments per warp pass)
+            env.close()
+            n2 = 20
+            env2 = pkg.UAVVecEnv(E, grid_size=grid, num_sensors=n2, precision="f32", rng="philox", seed=20261018,
+                                 env_id_offset=rank * E, auto_reset=True, device=str(dev), action_mask=False)
+            env2.reset_tensors()
+            for t in range(5):
+                env2.step_tensors(actions[t % n_act])
+            torch.cuda.synchronize(dev)
+            k2 = min(args.steps, 300)
+            ev0.record(stream)
+            for t in range(k2):
+                env2.step_tensors(actions[t % n_act])
+            ev1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms2 = ev0.elapsed_time(ev1) / k2
+            bpe2 = bytes_per_env_step(n2, "f32")
+            secondary = {"num_sensors": n2, "envs_per_gpu": E, "steps": k2, "ms_per_step": ms2,
+                         "value_per_gpu": E / (ms2 * 1e-3), "bytes_per_env_step": bpe2,
+                         "roofline_frac": bpe2 * E / (ms2 * 1e-3) / 1e9 / peak,
+                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=1, FPS=3, STACK=false, LEAN=true, PAIR=true>"}
+            env2.close()
         total_steps = E * world * args.steps
         line = {
             "metric": METRIC, "value": total_steps / (ms_max * 1e-3), "unit": METRIC, "n_gpus": world,
@@ -339,6 +363,7 @@ def run_gpu_arm(args):
                          "launch_ms": launch_ms},
             "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cpu_baseline_native": cpu_c,
+            "secondary_n20_rank0": secondary,
             "episode_stats": {"episodes_finished": float(sums[-1].item()),
                               "mean_return": float(sums[0].item() / max(sums[-1].item(), 1.0))},
         }
@@ -359,6 +384,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the N=20 secondary measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

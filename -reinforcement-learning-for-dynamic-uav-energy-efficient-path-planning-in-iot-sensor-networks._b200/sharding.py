@@ -1,7 +1,7 @@
 """Multi-GPU sharding of the batched environments.
 
 Environments never interact (the reference's DummyVecEnv just loops over them, dqn.py:1276), so the
-global id range [0, E) is cut into contiguous equal shards, one per rank / GPU; the step needs no
+global id range [0, E) is cut into contiguous near-equal shards (whole environment pairs), one per rank / GPU; the step needs no
 communication.  The only exchange is one all-reduce(sum) of the episode-statistic sums that the step
 kernel accumulates on each device (`UAVVecEnv.stat_sums`, float64[21]) -- the batched analogue of
 `CurriculumCallback._on_step` averaging `last_episode_stats` over workers (dqn.py:929-1039).  It is a
@@ -21,15 +21,21 @@ from ._native import STAT_COUNT, STAT_NAMES, STAT_SUMS
 
 
 def shard_range(global_envs: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous [start, stop) of global env ids owned by `rank`; the first `global_envs % world`
-    ranks own one extra environment."""
+    """Contiguous [start, stop) of global env ids owned by `rank`.  Shards are cut in units of environment PAIRS
+    (ids 2m, 2m+1): with up to 32 sensors per environment the observation draws of a pair come from one Philox
+    call, so a pair must live on one device and every shard starts at an even id (`env_id_offset` even).  Shard
+    sizes differ by at most 2."""
     if not (0 <= rank < world):
         raise ValueError("rank %d outside world of %d" % (rank, world))
     if global_envs < world:
         raise ValueError("fewer environments (%d) than ranks (%d)" % (global_envs, world))
-    base, extra = divmod(global_envs, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    pairs = (global_envs + 1) // 2
+    if pairs < world:
+        raise ValueError("fewer environment pairs (%d) than ranks (%d)" % (pairs, world))
+    base, extra = divmod(pairs, world)
+    first = rank * base + min(rank, extra)
+    last = first + base + (1 if rank < extra else 0)
+    return 2 * first, min(2 * last, global_envs)
 
 
 def make_sharded_env(pkg_env_cls, global_envs: int, rank: Optional[int] = None, world: Optional[int] = None,

@@ -65,7 +65,7 @@ def test_two_ranks_partition_and_single_allreduce(global_envs):
         assert p.exitcode == 0
     owned, stats, ncalls, r0 = q.get()
     assert owned == [1] * global_envs                       # disjoint and complete
-    assert r0 == (0, (global_envs + 1) // 2)
+    assert r0 == (0, 2 * (((global_envs + 1) // 2 + 1) // 2))   # whole environment pairs: rank 0 owns ceil(pairs / 2) of them
     assert ncalls == 1                                       # the path's only collective
     assert stats["episodes"] == 30.0
     assert abs(stats["return"] - (100.0 * 10 + 200.0 * 20) / 30.0) < 1e-12
@@ -81,11 +81,14 @@ def test_shard_range_properties():
             for a, b in zip(spans, spans[1:]):
                 assert a[1] == b[0]
             sizes = [b - a for a, b in spans]
-            assert max(sizes) - min(sizes) <= 1
+            assert max(sizes) - min(sizes) <= 2
+            assert all(a % 2 == 0 for a, _ in spans)        # environment pairs never straddle shards
     with pytest.raises(ValueError):
         pkg.shard_range(4, 4, 4)
     with pytest.raises(ValueError):
         pkg.shard_range(3, 0, 8)
+    with pytest.raises(ValueError):
+        pkg.shard_range(5, 0, 4)                            # 3 pairs cannot feed 4 ranks
 
 
 def test_single_process_stats_need_no_process_group():

@@ -74,7 +74,7 @@ def test_two_ranks_partition_and_single_allreduce(global_envs):
 
 def test_shard_range_properties():
     pkg = import_package()
-    for E in (8, 1000, 1 << 20, (1 << 20) + 3):
+    for E in (16, 1000, 1 << 20, (1 << 20) + 3):
         for world in (1, 2, 4, 8):
             spans = [pkg.shard_range(E, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == E

@@ -24,7 +24,7 @@ def shard_range(global_envs: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [start, stop) of global env ids owned by `rank`.  Shards are cut in units of environment PAIRS
     (ids 2m, 2m+1): with up to 32 sensors per environment the observation draws of a pair come from one Philox
     call, so a pair must live on one device and every shard starts at an even id (`env_id_offset` even).  Shard
-    sizes differ by at most 2."""
+    sizes differ by at most 3 (one pair, plus the unpaired last environment of an odd total)."""
     if not (0 <= rank < world):
         raise ValueError("rank %d outside world of %d" % (rank, world))
     if global_envs < world:

@@ -263,6 +263,8 @@ struct uavsim_handle {
     Layout lay;
     char* arena = nullptr;
     bool owns_arena = false;
+    unsigned* tickets = nullptr;  // two tile-ticket counters of the step kernel (deliberately NOT in the arena: a
+                                  // snapshot / restore of the arena must not rewind them)
     Params<double> p64;
     Params<float> p32;
     Buffers buf;
@@ -388,6 +390,15 @@ int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, v
         }
         h->owns_arena = true;
     }
+    {
+        cudaError_t e = cudaMalloc((void**)&h->tickets, 2 * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->tickets, 0, 2 * sizeof(unsigned), st);
+        if (e != cudaSuccess) {
+            if (h->owns_arena) cudaFree(h->arena);
+            delete h;
+            return cuda_fail(e, "cudaMalloc(tile tickets)");
+        }
+    }
     h->p64 = make_params<double>(*c);
     h->p32 = make_params<float>(*c);
     Buffers& b = h->buf;
@@ -399,6 +410,8 @@ int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, v
     b.ssf = (uint8_t*)(h->arena + h->lay.ssf);
     b.stat_sums = (double*)(h->arena + h->lay.stat_sums);
     b.error_word = (unsigned long long*)(h->arena + h->lay.error_word);
+    b.tile_ticket = h->tickets;
+    b.tile = UAVSIM_TILE;
     b.E = c->num_envs;
     h->actions_dev = (int32_t*)(h->arena + h->lay.actions);
     cudaError_t e = cudaMemsetAsync(h->arena, 0, (size_t)h->lay.total, st);
@@ -412,6 +425,7 @@ int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, v
     }
     if (e != cudaSuccess) {
         if (h->owns_arena) cudaFree(h->arena);
+        cudaFree(h->tickets);
         delete h;
         return cuda_fail(e, "arena initialisation");
     }
@@ -422,6 +436,7 @@ int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, v
 int uavsim_destroy(uavsim_handle* h) {
     if (!h) return UAVSIM_OK;
     if (h->owns_arena) cudaFree(h->arena);
+    cudaFree(h->tickets);
     delete h;
     return UAVSIM_OK;
 }

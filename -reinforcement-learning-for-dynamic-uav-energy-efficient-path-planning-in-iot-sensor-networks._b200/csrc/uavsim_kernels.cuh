@@ -119,6 +119,8 @@ struct Buffers {
     int32_t E;
     uint32_t step_serial;
     int32_t frame_slot;  // row of the (2k-row mirrored ring) frame block this launch writes
+    int32_t tile;        // environments per tile of this launch (2, 4, 8 or 16 <= kTile; chosen by the launcher)
+    unsigned* tile_ticket;  // two tile counters (this launch / zeroed for the next), outside the arena
 };
 
 // Frame stacking (VecFrameStack, dqn.py:1278; extractor layout dqn.py:612-620) without a shift pass: each
@@ -1778,7 +1780,7 @@ __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real
 template <typename Real>
 __device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* actions, int base, int tb, int lane,
                                            TileSmem<Real>& ts) {
-    const int n = min(kTile, b.E - base);
+    const int n = min(b.tile, b.E - base);
 #pragma unroll
     for (int r = 0; r < kTile; ++r)
         if (r < n) cp_async4(&ts.rec[tb][r][lane ^ r], reinterpret_cast<const uint32_t*>(b.rec + base + r) + lane);
@@ -2036,8 +2038,21 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     // carried in registers: with 184 KB of the SM given to shared memory the L1 is small and a spilled
     // loop-carried value costs an L2 round trip per environment
 #define UAVSIM_E (b.E)
-#define UAVSIM_TILE_STRIDE ((int)gridDim.x * step_warps<Real, SPL, PAIR>() * kTile)
-    int base = (blockIdx.x * step_warps<Real, SPL, PAIR>() + warp) * kTile;
+    // Tiles are handed out by TICKET (one atomicAdd per tile per warp, requested a whole tile ahead of its use):
+    // warps that drew cheap tiles (few collect actions, few restarts) take more of them, so the launch does not end
+    // on the slowest statically assigned warp, and small batches spread over the whole machine with a smaller tile.
+    // Two counters alternate between launches: this one counts, the other is zeroed for the next launch.
+    unsigned* const ticket_ctr = b.tile_ticket + (b.step_serial & 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.tile_ticket[(b.step_serial & 1u) ^ 1u] = 0u;
+#define UAVSIM_TAKE_TICKET() ((lane == 0) ? (int)atomicAdd(ticket_ctr, 1u) : 0)
+    int base, next_base;
+    {
+        const int t0 = UAVSIM_TAKE_TICKET();
+        const int t1 = UAVSIM_TAKE_TICKET();
+        base = shfl(t0, 0) * b.tile;
+        next_base = shfl(t1, 0) * b.tile;
+    }
+#define UAVSIM_NEXT_BASE next_base
     int tb = 0;  // tile buffer in use
     constexpr bool kBulk = kStaged && (UAVSIM_BULK_STAGE != 0);  // sensor columns by bulk copy + mbarrier
     constexpr bool kRowObs = kStaged && (UAVSIM_ROW_OBS != 0);   // observation row staged in smem, coalesced store
@@ -2068,8 +2083,9 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         }
     }
 
-    for (; base < UAVSIM_E; base += UAVSIM_TILE_STRIDE) {
-        const int ntile = min(kTile, UAVSIM_E - base);
+    while (base < UAVSIM_E) {
+        const int pending_ticket = UAVSIM_TAKE_TICKET();  // the tile after the next one; consumed at the end of this tile
+        const int ntile = min(b.tile, UAVSIM_E - base);
         uint32_t(*rec)[32] = ts.rec[tb];
         if constexpr (!kStaged) {
             // ---- tile records: global -> swizzled shared memory (lane = word: coalesced 128-byte rows) ----
@@ -2165,7 +2181,9 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                         hb = true;
                     }
                 } else {
-                    e1 = base + UAVSIM_TILE_STRIDE;
+                    e1 = UAVSIM_NEXT_BASE;
+                    cp_async_wait<0>();  // the next tile's records (T) must have landed before they are read; with
+                    __syncwarp();        // the 16-tile they did long ago, with a short tile this is the only guarantee
                     if (e1 < UAVSIM_E) {
                         n1a = (int)ts.rec[tb ^ 1][0][kRN];
                         ha = true;
@@ -2179,8 +2197,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 if (hb) stage_issue<Real, SPL>(b, p, e1 + 1, n1b, lane, stage[(pb ^ 1) * 2 + 1]);
                 cp_async_commit();
                 if (k == 0) {
-                    if (base + UAVSIM_TILE_STRIDE < UAVSIM_E)
-                        tile_issue<Real>(b, actions, base + UAVSIM_TILE_STRIDE, tb ^ 1, lane, ts);
+                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
                     cp_async_commit();
                 }
                 if (k <= 2)
@@ -2204,15 +2222,15 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 if (k + 1 < ntile) {
                     n1 = (int)rec[k + 1][kRN ^ (k + 1)];
                 } else {
-                    e1 = base + UAVSIM_TILE_STRIDE;
+                    e1 = UAVSIM_NEXT_BASE;
                     cp_async_wait<0>();
                     __syncwarp();
                     if (e1 < UAVSIM_E) n1 = (int)ts.rec[tb ^ 1][0][kRN];
                 }
                 if (e1 < UAVSIM_E) stage_issue_bulk<Real, SPL>(b, p, e1, n1, lane, stage[(it & 1) ^ 1], &mine.bar[(it & 1) ^ 1]);
                 if (k == 1) {
-                    if (base + UAVSIM_TILE_STRIDE < UAVSIM_E)
-                        tile_issue<Real>(b, actions, base + UAVSIM_TILE_STRIDE, tb ^ 1, lane, ts);
+                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
                     cp_async_commit();
                 }
                 mbar_wait(&mine.bar[it & 1], (it >> 1) & 1u);
@@ -2227,25 +2245,26 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 // CURRENT environment's stage (issued one iteration ago)
                 // the stage buffers alternate with k: tiles hold an even number of environments (a partial
                 // tile can only be a warp's last one), so buffer k & 1 is always the one staged for slot k
-                // The NEXT tile's records + actions are requested at k == 1 (one more group in flight for two
-                // iterations) and have landed long before k reaches the end of the tile.
+                // The NEXT tile's records + actions (T) are requested at k == 0.
                 int e1 = e + 1, n1 = 0;
                 if (k + 1 < ntile) {
                     n1 = (int)rec[k + 1][kRN ^ (k + 1)];
                 } else {
-                    e1 = base + UAVSIM_TILE_STRIDE;
+                    e1 = UAVSIM_NEXT_BASE;
+                    cp_async_wait<0>();  // the next tile's records (T) must have landed before they are read
+                    __syncwarp();
                     if (e1 < UAVSIM_E) n1 = (int)ts.rec[tb ^ 1][0][kRN];
                 }
                 if (e1 < UAVSIM_E)
                     stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[(k & 1) ^ 1]);
                 cp_async_commit();
-                if (k == 1) {
-                    if (base + UAVSIM_TILE_STRIDE < UAVSIM_E)
-                        tile_issue<Real>(b, actions, base + UAVSIM_TILE_STRIDE, tb ^ 1, lane, ts);
+                if (k == 0) {  // T: the other record buffer is free since the previous tile's write-back
+                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
                     cp_async_commit();
                 }
-                if (k == 1 || k == 2)
-                    cp_async_wait<2>();
+                if (k < 2)
+                    cp_async_wait<2>();  // commit order G(k-1), [T,] G(k): this environment's stage is G(k-1)
                 else
                     cp_async_wait<1>();
                 __syncwarp();
@@ -2450,9 +2469,12 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             __syncwarp();
             tb ^= 1;
         }
+        base = next_base;
+        next_base = shfl(pending_ticket, 0) * b.tile;
     }
 #undef UAVSIM_E
-#undef UAVSIM_TILE_STRIDE
+#undef UAVSIM_NEXT_BASE
+#undef UAVSIM_TAKE_TICKET
 }
 
 }  // namespace uavsim

@@ -26,34 +26,57 @@ cudaError_t launch_max_throughput_greedy_f64(const Params<double>& p, const Buff
 cudaError_t launch_max_throughput_greedy_f32(const Params<float>& p, const Buffers& b, const double* probe_draws,
                                               int32_t* actions, bool replay, cudaStream_t st);
 
-// Persistent grid: one wave of blocks at full residency (SM count x occupancy), never more blocks than
-// there are groups of kWarpsPerBlock environments.
+// Blocks of `k` resident at once on the current device (SM count x occupancy).
 template <typename Kernel>
-inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_warp = 1, int warps = kWarpsPerBlock) {
+inline int resident_blocks(Kernel k, size_t dyn_smem, int warps) {
     // keyed by (kernel, device): different instantiations share a function-pointer TYPE, so a plain
     // function-local static would be shared between them
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, int> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    int blocks_per_wave = 0;
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find({(const void*)k, dev});
-        if (it != cache.end()) blocks_per_wave = it->second;
+        if (it != cache.end()) return it->second;
     }
-    if (blocks_per_wave == 0) {
-        int sms = 0, occ = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 32 * warps, dyn_smem);
-        blocks_per_wave = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
-        std::lock_guard<std::mutex> lock(mu);
-        cache[{(const void*)k, dev}] = blocks_per_wave;
-    }
+    int sms = 0, occ = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 32 * warps, dyn_smem);
+    const int blocks = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
+    std::lock_guard<std::mutex> lock(mu);
+    cache[{(const void*)k, dev}] = blocks;
+    return blocks;
+}
+
+// Persistent grid: one wave of blocks at full residency, never more blocks than there are groups of
+// warps x envs_per_warp environments.
+template <typename Kernel>
+inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_warp = 1, int warps = kWarpsPerBlock) {
+    const int blocks_per_wave = resident_blocks(k, dyn_smem, warps);
     const int per_block = warps * envs_per_warp;
     const int need = (E + per_block - 1) / per_block;
     return need < blocks_per_wave ? need : blocks_per_wave;
+}
+
+// Environments per tile of a step launch: 16 when every resident warp gets at least ~2.5 tiles, else the largest
+// smaller tile that does (phases A / C run one environment per lane, so a smaller tile costs a few per cent per
+// environment but lets a small batch use the whole machine).  The pair kernel needs a multiple of 4.
+inline int choose_tile(int E, int resident_warps, bool pair) {
+    for (int t = kTile; t >= (pair ? 4 : 2); t >>= 1)
+        if ((double)E >= 2.5 * (double)t * (double)resident_warps) return t;
+    return pair ? 4 : 2;
+}
+
+template <typename Kernel>
+inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool pair, const Buffers& b, dim3* grid, Buffers* bb) {
+    const int blocks = resident_blocks(k, smem, warps);
+    *bb = b;
+    bb->tile = choose_tile(b.E, blocks * warps, pair);
+    const int per_block = warps * bb->tile;
+    const int need = (b.E + per_block - 1) / per_block;
+    *grid = dim3((unsigned)(need < blocks ? need : blocks));
 }
 
 template <typename Real>
@@ -74,12 +97,18 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
                 constexpr size_t smem = step_smem_bytes<Real, 2>();
                 constexpr int warps = step_warps<Real, 2>();
                 auto k = stack ? step_kernel<Real, false, 2, 3, true, true> : step_kernel<Real, false, 2, 3, false, true>;
-                k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
+                dim3 grid;
+                Buffers bb;
+                launch_step_kernel(k, smem, warps, false, b, &grid, &bb);
+                k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);
             } else {  // P <= 32: two environments per warp pass (uavsim_kernels.cuh, pair_phase)
                 constexpr size_t smem = step_smem_bytes<Real, 1, true>();
                 constexpr int warps = step_warps<Real, 1, true>();
                 auto k = stack ? step_kernel<Real, false, 1, 3, true, true, true> : step_kernel<Real, false, 1, 3, false, true, true>;
-                k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions);
+                dim3 grid;
+                Buffers bb;
+                launch_step_kernel(k, smem, warps, true, b, &grid, &bb);
+                k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);
             }
             return cudaGetLastError();
         }
@@ -91,7 +120,10 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
         auto k = p.fps == 5 ? (stack ? step_kernel<Real, R, S, 5, true> : step_kernel<Real, R, S, 5, false>)  \
                             : (stack ? step_kernel<Real, R, S, 3, true> : step_kernel<Real, R, S, 3, false>); \
         constexpr int warps = step_warps<Real, S>();                                          \
-        k<<<persistent_grid(k, b.E, smem, kTile, warps), 32 * warps, smem, st>>>(p, b, actions); \
+        dim3 grid;                                                                            \
+        Buffers bb;                                                                           \
+        launch_step_kernel(k, smem, warps, false, b, &grid, &bb);                             \
+        k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                    \
     } while (0)
     if (replay) {
         if (two)

@@ -2049,8 +2049,11 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     {
         const int t0 = UAVSIM_TAKE_TICKET();
         const int t1 = UAVSIM_TAKE_TICKET();
-        base = shfl(t0, 0) * b.tile;
-        next_base = shfl(t1, 0) * b.tile;
+        // redux.sync (REDUX) delivers its result in a UNIFORM register: the compiler then knows that base, the
+        // environment index, the row offsets and the loop counters derived from them are warp-uniform, keeps them
+        // off the vector register file and turns the loop-control branches into uniform branches
+        base = (int)__reduce_max_sync(kFull, (unsigned)t0) * b.tile;
+        next_base = (int)__reduce_max_sync(kFull, (unsigned)t1) * b.tile;
     }
 #define UAVSIM_NEXT_BASE next_base
     int tb = 0;  // tile buffer in use
@@ -2470,7 +2473,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             tb ^= 1;
         }
         base = next_base;
-        next_base = shfl(pending_ticket, 0) * b.tile;
+        next_base = (int)__reduce_max_sync(kFull, (unsigned)pending_ticket) * b.tile;
     }
 #undef UAVSIM_E
 #undef UAVSIM_NEXT_BASE

@@ -143,3 +143,14 @@ def test_config2_full_episodes_to_truncation(pkg):
                           compare_every=64)
     _check(res)
     assert res["dones"] >= 1024, res
+
+
+@pytest.mark.parametrize("N", [1, 2, 32, 33, 64])
+def test_sensor_count_edges(pkg, N):
+    """Sensor counts at the edges of the lane mapping: a single sensor (no fairness variance, reward_function.py:49),
+    exactly one / just over one slot per lane, and the 64-sensor maximum."""
+    from parity_util import run_parity_case
+    res = run_parity_case(pkg, E=96, N=N, grid=(120, 120), steps=40, seed=100 + N, p_collect=0.6, start=(60.0, 60.0),
+                          auto_reset=True, params_over=dict(max_battery=3.0), ref_kwargs=dict(max_battery=3.0))
+    _check(res)
+    assert res["dones"] > 0, res

@@ -1951,8 +1951,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
         valid[q] = flags[q] & kFlagValid;
         collect[q] = flags[q] & kFlagCollect;
         N[q] = valid[q] ? ts.N[k] : 0;  // an absent / rejected environment has no active lane: nothing is reduced or stored
-        const uint32_t row = (uint32_t)(base + k) * (uint32_t)p.P;
-        load_sensors_staged<float, 1>(st2[q], N[q], lane, reinterpret_cast<View>(s[q]), (int)(row & 1u), (int)(row & 3u));
+        load_sensors_staged<float, 1>(st2[q], N[q], lane, reinterpret_cast<View>(s[q]));  // (cp.async stages: no row offset)
     }
     __syncwarp();
     if (!(valid[0] || valid[1])) return;

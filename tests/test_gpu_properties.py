@@ -127,7 +127,7 @@ def test_shard_invariance_checksum_of_checksums(pkg):
     np.testing.assert_allclose(whole[:, 2], sum(p[:, 2] for p in parts), rtol=1e-12)
 
 
-@pytest.mark.parametrize("N,stack", [(20, 1), (50, 1), (50, 4), (33, 1)])
+@pytest.mark.parametrize("N,stack", [(20, 1), (50, 1), (50, 4), (33, 1), (1, 1), (2, 1), (32, 1), (16, 4), (64, 1), (10, 1), (30, 4), (31, 1)])
 def test_lean_instantiation_equals_the_diagnostic_one(pkg, N, stack):
     """The benchmarked kernel is the LEAN instantiation (optional features compiled out); the instantiation with
     parity diagnostics attached is the one the oracle-replay tests exercise.  Same seed, same actions: state,

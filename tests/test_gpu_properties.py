@@ -166,3 +166,32 @@ def test_lean_instantiation_equals_the_diagnostic_one(pkg, N, stack):
         assert (rl[k] == rd[k]).all() or np.array_equal(rl[k], rd[k], equal_nan=True), k
     lean.close()
     diag.close()
+
+
+def test_pair_kernel_with_per_env_sensor_counts(pkg):
+    """Two environments of a pair may have different sensor counts (DQN workers are pinned to 10/20/30, dqn.py:1066):
+    the pair kernel against the one-slot diagnostic kernel, bit for bit."""
+    import torch
+    E, T = 2051, 120
+    ns = np.resize(np.array([10, 20, 30, 7, 32, 1], dtype=np.int32), E)
+    kw = dict(grid_size=(250, 250), num_sensors=ns, max_sensors=32, seed=77, max_battery=9.0, precision="f32", rng="philox",
+              uav_start_position=(120.0, 130.0))
+    lean = pkg.UAVVecEnv(E, **kw)
+    diag = pkg.UAVVecEnv(E, step_detail=True, **kw)
+    lean.reset_tensors()
+    diag.reset_tensors()
+    g = torch.Generator(device=lean.device)
+    g.manual_seed(9)
+    for t in range(T):
+        a = torch.randint(0, 5, (E,), dtype=torch.int32, device=lean.device, generator=g)
+        a = torch.where(torch.rand(E, device=lean.device, generator=g) < 0.4, torch.full_like(a, 4), a)
+        lean.step_tensors(a)
+        diag.step_tensors(a)
+        assert torch.equal(lean.reward, diag.reward), t
+        assert torch.equal(lean.obs, diag.obs), t
+    assert int(lean.stat_sums[-1].item()) > E // 2
+    sl, sd = lean.state(), diag.state()
+    for k in sl:
+        assert torch.equal(torch.nan_to_num(sl[k].double()), torch.nan_to_num(sd[k].double())), k
+    lean.close()
+    diag.close()

@@ -684,18 +684,14 @@ __device__ __forceinline__ uint8_t action_mask_of(float x, float y, int W, int H
 template <typename Real, int SPL, int FPS, bool HEAD, bool MIRROR>
 __device__ __forceinline__ void observe_with(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
                                              const Real (&dd)[SPL], const Real (&de)[SPL], int lane,
-                                             float* __restrict__ out, float* srow);
+                                             float* __restrict__ out);
 
-// srow != nullptr (staged step path): the features go to a row image in shared memory instead, and the caller
-// writes the row to HBM with consecutive lanes on consecutive floats (store_obs_row) -- a lane-per-sensor store
-// with a stride of FPS floats touches 12 sectors per instruction and leaves the merging to L1/L2.
 template <typename Real, bool REPLAY, int SPL, int FPS, bool HEAD, bool MIRROR>
 __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
-                                        const Draws<Real, REPLAY, SPL>& dr, int lane, float* __restrict__ out,
-                                        float* srow = nullptr) {
+                                        const Draws<Real, REPLAY, SPL>& dr, int lane, float* __restrict__ out) {
     Real dd[SPL], de[SPL];
     dr.obs(p, lane, dd, de);
-    observe_with<Real, SPL, FPS, HEAD, MIRROR>(p, h, s, dd, de, lane, out, srow);
+    observe_with<Real, SPL, FPS, HEAD, MIRROR>(p, h, s, dd, de, lane, out);
 }
 
 // The observation pass with the D / E draws already in hand (the pair kernel makes one Philox call for two
@@ -703,7 +699,7 @@ __device__ __forceinline__ void observe(const Params<Real>& p, const Hot& h, Sen
 template <typename Real, int SPL, int FPS, bool HEAD, bool MIRROR>
 __device__ __forceinline__ void observe_with(const Params<Real>& p, const Hot& h, Sensor<Real> (&s)[SPL],
                                              const Real (&dd)[SPL], const Real (&de)[SPL], int lane,
-                                             float* __restrict__ out, float* srow) {
+                                             float* __restrict__ out) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     const int mirror = MIRROR ? p.frame_mirror : 0;
     float inv_w = 0.f, inv_h = 0.f;
@@ -764,12 +760,7 @@ __device__ __forceinline__ void observe_with(const Params<Real>& p, const Hot& h
                     f[4] = ry;
                 }
             }
-            if (srow) {
-                if (s[k].active) {
-#pragma unroll
-                    for (int q = 0; q < FPS; ++q) srow[3 + FPS * j + q] = f[q];
-                }
-            } else if (s[k].active) {
+            if (s[k].active) {
 #pragma unroll
                 for (int q = 0; q < FPS; ++q) {
                     o[q] = f[q];
@@ -1516,57 +1507,15 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
 // next environment (i + total_warps) stream from HBM into a shared-memory stage with cp.async
 // (LDGSTS: no registers held, no stall until the data is needed), double buffered per warp.
 // ------------------------------------------------------------------------------------------------
-// A stage holds one environment's sensor columns.  The bulk copies start at 16-byte-aligned global addresses:
-// the rows of the 8-byte position column and the 4-byte generated column start at e*P*8 / e*P*4 bytes, which is
-// not always a multiple of 16, so those copies begin at the aligned address below the row and the stage keeps
-// 16 bytes of slack; lanes index with the row's element offset (stage_offsets).
+// A stage holds one environment's sensor columns.  (Tried and removed, commit 0510d7b: TMA bulk copies onto an
+// mbarrier -- three 320-800 B `cp.async.bulk` per environment keep the SM's TMA unit ~2/3 busy and were 3-12 %
+// slower than per-lane cp.async -- and a shared-memory row image for coalesced observation stores, 7 % slower.)
 template <typename Real, int SPL>
 struct alignas(alignof(SensorState<Real>) > 16 ? alignof(SensorState<Real>) : 16) StageBuf {
     SensorState<Real> st[32 * SPL];
-    float2 pos[32 * SPL + 2];
-    Real gen[32 * SPL + 16 / sizeof(Real)];
+    float2 pos[32 * SPL];
+    Real gen[32 * SPL];
 };
-
-// Measured (profiles/README.md): three small bulk copies per environment keep the SM's TMA unit ~2/3 busy
-// (~46 cycles of service per operation) and the mbarrier waits become exposed -- 3 % slower at N=50, 12 % at N=20
-// than per-lane cp.async.  The bulk pipeline stays selectable for row sizes where it pays.
-#ifndef UAVSIM_BULK_STAGE
-#define UAVSIM_BULK_STAGE 0
-#endif
-// Likewise measured: staging the observation row in shared memory for fully coalesced stores costs more issue
-// slots (+STS/LDS/syncwarp) than the partial-sector stores it removes -- 7 % slower at N=50.  Off by default.
-#ifndef UAVSIM_ROW_OBS
-#define UAVSIM_ROW_OBS 0
-#endif
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// mbarrier + bulk asynchronous copy (TMA engine, SASS UBLKCP): ONE lane moves a whole column row; the bytes
-// landing complete the transaction count the same lane armed on the stage's mbarrier.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
@@ -1603,29 +1552,8 @@ __device__ __forceinline__ void stage_issue(const Buffers& b, const Params<Real>
     }
 }
 
-// Bulk version: lane 0 arms the stage's mbarrier with the byte count and issues three bulk copies (state row,
-// position row, generated row) of environment e.
 template <typename Real, int SPL>
-__device__ __forceinline__ void stage_issue_bulk(const Buffers& b, const Params<Real>& p, int e, int N, int lane,
-                                                 StageBuf<Real, SPL>& sb, uint64_t* bar) {
-    static_assert(sizeof(SensorState<Real>) == 16, "the staged pipeline is built for the float32 layout");
-    if (lane == 0) {
-        const uint32_t row = (uint32_t)e * (uint32_t)p.P;
-        const char* gs = reinterpret_cast<const char*>(b.sstate) + (size_t)row * 16u;
-        const char* gp = reinterpret_cast<const char*>(b.spos) + (size_t)row * 8u;
-        const char* gg = reinterpret_cast<const char*>(b.sgen) + (size_t)row * 4u;
-        const uint32_t po = (row * 8u) & 15u, go = (row * 4u) & 15u;  // the columns themselves are 256-byte aligned
-        const uint32_t bs = (uint32_t)N * 16u, bp = (po + (uint32_t)N * 8u + 15u) & ~15u, bg = (go + (uint32_t)N * 4u + 15u) & ~15u;
-        mbar_expect_tx(bar, bs + bp + bg);
-        bulk_g2s(sb.st, gs, bs, bar);
-        bulk_g2s(sb.pos, gp - po, bp, bar);
-        bulk_g2s(sb.gen, gg - go, bg, bar);
-    }
-}
-
-template <typename Real, int SPL>
-__device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& sb, int N, int lane, Sensor<Real> (&s)[SPL],
-                                                    int pos_off = 0, int gen_off = 0) {
+__device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& sb, int N, int lane, Sensor<Real> (&s)[SPL]) {
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         const int j = lane + 32 * k;
@@ -1637,8 +1565,8 @@ __device__ __forceinline__ void load_sensors_staged(const StageBuf<Real, SPL>& s
         // environment left there and runs the same arithmetic on it -- every reduction, ballot and store is
         // masked by `active`, so the values never escape.
         const SensorState<Real> v = sb.st[j];
-        const float2 xy = sb.pos[j + pos_off];
-        const Real g = sb.gen[j + gen_off];
+        const float2 xy = sb.pos[j];
+        const Real g = sb.gen[j];
         float ema;
         int sf;
         unpack_sf(v.ema, ema, sf);
@@ -1714,7 +1642,6 @@ struct alignas(alignof(SensorState<Real>) > 16 ? alignof(SensorState<Real>) : 16
     WarpSmem ws;
     TileSmem<Real> ts;
     StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : (PAIR ? 4 : 2)];  // pair kernel: 2 stages x 2 envs
-    uint64_t bar[2];  // one mbarrier per stage (bulk-copy pipeline)
 };
 template <typename Real, int SPL, bool PAIR = false>
 constexpr size_t step_smem_bytes() {
@@ -1787,28 +1714,12 @@ __device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* acti
     if (lane < n) cp_async4(&ts.action[tb][lane], actions + base + lane);
 }
 
-// Row image in shared memory -> observation row in HBM, lane i on float i (+32, +64, ...): 128 contiguous bytes
-// per instruction.  n = 3 + FPS * N floats (ghost slots stay as zeroed at reset).
-template <int SPL, int FPS, bool MIRROR>
-__device__ __forceinline__ void store_obs_row(const float* srow, float* __restrict__ out, int n, int mirror, int lane) {
-    constexpr int kIters = (3 + FPS * 32 * SPL + 31) / 32;
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-        const int i = lane + 32 * it;
-        if (i < n) {
-            const float v = srow[i];
-            out[i] = v;
-            if constexpr (MIRROR) out[i + mirror] = v;
-        }
-    }
-}
-
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
 // the environment are read from the tile block where they are used and results are written back as soon as
 // they exist, so that little besides the sensor registers is live across the phase.
 template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN>
 __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
-                                             int tb, int k, int e, int lane, Sensor<Real> (&s)[SPL], float* srow = nullptr) {
+                                             int tb, int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     const int flags = ts.flags[k];
     const bool collect = flags & kFlagCollect;
@@ -1868,17 +1779,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
         h.vis_lo = collect ? ts.nvis_lo[k] : ts.vis_lo[k];  // relational rows carry the visited flag
         h.vis_hi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
         observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e), lane,
-                                                       obs_frame(p, b, e), srow);
-        if (srow) {  // staged path: head (uav_env.py:644) + coalesced row store
-            if (lane == 0) {
-                srow[0] = __fdividef(h.x, (float)h.W);
-                srow[1] = __fdividef(h.y, (float)h.H);
-                srow[2] = (float)ts.battery[k] * p.inv_max_battery;
-            }
-            __syncwarp();
-            store_obs_row<SPL, FPS, STACK>(srow, obs_frame(p, b, e), 3 + FPS * N, STACK ? p.frame_mirror : 0, lane);
-            __syncwarp();  // the row image lives in the stage that a later iteration refills
-        }
+                                                       obs_frame(p, b, e));
     }
 
     // ---- RelationalUAVEnv.step supplements (env_wrapper.py:169-198): potential distance, dwell probes ----
@@ -1951,7 +1852,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
         valid[q] = flags[q] & kFlagValid;
         collect[q] = flags[q] & kFlagCollect;
         N[q] = valid[q] ? ts.N[k] : 0;  // an absent / rejected environment has no active lane: nothing is reduced or stored
-        load_sensors_staged<float, 1>(st2[q], N[q], lane, reinterpret_cast<View>(s[q]));  // (cp.async stages: no row offset)
+        load_sensors_staged<float, 1>(st2[q], N[q], lane, reinterpret_cast<View>(s[q]));
     }
     __syncwarp();
     if (!(valid[0] || valid[1])) return;
@@ -2010,7 +1911,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
             h.battery = 0.0;
             h.vis_lo = h.vis_hi = 0u;
             observe_with<float, 1, 3, false, STACK>(p, h, reinterpret_cast<View>(s[q]), dd[q], de[q], lane,
-                                                    obs_frame(p, b, base + k0 + q), nullptr);
+                                                    obs_frame(p, b, base + k0 + q));
         }
     }
 #pragma unroll
@@ -2056,22 +1957,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     }
 #define UAVSIM_NEXT_BASE next_base
     int tb = 0;  // tile buffer in use
-    constexpr bool kBulk = kStaged && (UAVSIM_BULK_STAGE != 0);  // sensor columns by bulk copy + mbarrier
-    constexpr bool kRowObs = kStaged && (UAVSIM_ROW_OBS != 0);   // observation row staged in smem, coalesced store
-    uint32_t it = 0;  // environments this warp has consumed: stage = it & 1, mbarrier phase parity = (it >> 1) & 1
     if constexpr (kStaged) {  // prime both pipelines: records of the first tile, sensor columns of its first env
-        if constexpr (kBulk) {
-            if (lane == 0) {
-                mbar_init(&mine.bar[0], 1);
-                mbar_init(&mine.bar[1], 1);
-                mbar_fence_init();
-            }
-            __syncwarp();
-            if (base < UAVSIM_E) {
-                tile_issue<Real>(b, actions, base, 0, lane, ts);
-                stage_issue_bulk<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0], &mine.bar[0]);
-            }
-        } else if (base < UAVSIM_E) {
+        if (base < UAVSIM_E) {
             tile_issue<Real>(b, actions, base, 0, lane, ts);
             if constexpr (!PAIR) stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
         }
@@ -2215,34 +2102,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         for (int k = 0; !PAIR && k < ntile; ++k) {
             const int e = base + k;
             Sensor<Real> s[SPL];
-            if constexpr (kBulk) {
-                // Request the columns of the NEXT environment of this warp's sequence (one lane, three bulk copies
-                // onto the other stage's mbarrier), then wait on the CURRENT environment's mbarrier (armed one
-                // iteration ago).  The next tile's records + actions are requested with cp.async at k == 1 and
-                // retired before the last environment of the tile peeks at them.
-                int e1 = e + 1, n1 = 0;
-                if (k + 1 < ntile) {
-                    n1 = (int)rec[k + 1][kRN ^ (k + 1)];
-                } else {
-                    e1 = UAVSIM_NEXT_BASE;
-                    cp_async_wait<0>();
-                    __syncwarp();
-                    if (e1 < UAVSIM_E) n1 = (int)ts.rec[tb ^ 1][0][kRN];
-                }
-                if (e1 < UAVSIM_E) stage_issue_bulk<Real, SPL>(b, p, e1, n1, lane, stage[(it & 1) ^ 1], &mine.bar[(it & 1) ^ 1]);
-                if (k == 1) {
-                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
-                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
-                    cp_async_commit();
-                }
-                mbar_wait(&mine.bar[it & 1], (it >> 1) & 1u);
-                const StageBuf<Real, SPL>& cur = stage[it & 1];
-                ++it;
-                if (!(ts.flags[k] & kFlagValid)) continue;
-                const uint32_t row = (uint32_t)e * (uint32_t)p.P;
-                load_sensors_staged<Real, SPL>(cur, ts.N[k], lane, s, (int)(row & 1u), (int)(row & 3u));
-                __syncwarp();  // every lane has read the stage before a later iteration refills it
-            } else if constexpr (kStaged) {
+            if constexpr (kStaged) {
                 // launch the copies of the NEXT environment of this warp's sequence, then wait for the
                 // CURRENT environment's stage (issued one iteration ago)
                 // the stage buffers alternate with k: tiles hold an even number of environments (a partial
@@ -2279,9 +2139,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 if (!(ts.flags[k] & kFlagValid)) continue;
                 load_sensors<Real, SPL>(b, p, e, ts.N[k], lane, s);
             }
-            float* srow = nullptr;  // row image: the stage this environment was loaded from is free until refilled
-            if constexpr (kRowObs) srow = reinterpret_cast<float*>(kBulk ? &stage[(it - 1) & 1] : &stage[k & 1]);
-            sensor_phase<Real, REPLAY, SPL, FPS, STACK, LEAN>(p, b, ts, ws, tb, k, e, lane, s, srow);
+            sensor_phase<Real, REPLAY, SPL, FPS, STACK, LEAN>(p, b, ts, ws, tb, k, e, lane, s);
         }
         __syncwarp();
 
@@ -2420,15 +2278,13 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                     f0 = f0 + gx;
                     f1 = f1 + gy;
                 }
-                if constexpr (!kRowObs) {  // (the staged path wrote the whole row, head included, in phase B)
-                    o[0] = f0;
-                    o[1] = f1;
-                    o[2] = f2;
-                    if constexpr (STACK) {
-                        o[p.frame_mirror] = f0;
-                        o[p.frame_mirror + 1] = f1;
-                        o[p.frame_mirror + 2] = f2;
-                    }
+                o[0] = f0;
+                o[1] = f1;
+                o[2] = f2;
+                if constexpr (STACK) {
+                    o[p.frame_mirror] = f0;
+                    o[p.frame_mirror + 1] = f1;
+                    o[p.frame_mirror + 2] = f2;
                 }
                 if (b.action_mask && !restart) b.action_mask[e] = action_mask_of(x, y, R.i32(kRGridW), R.i32(kRGridH));
                 if (feat_step_detail<LEAN>(b)) {

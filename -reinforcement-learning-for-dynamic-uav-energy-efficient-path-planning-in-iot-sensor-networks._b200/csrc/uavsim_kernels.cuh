@@ -1215,43 +1215,45 @@ __device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& i
 template <typename Real>
 struct TileSmem;
 
+enum : int { kGeneric = 0, kLeanPlain = 1, kLeanDomainRand = 2 };
+
 // LEAN instantiations of the step kernel compile the optional features out (DomainRandEnv shaping, the
 // relational wrapper, draw export, parity diagnostics): the plain UAVEnvironment step -- the benchmarked
 // configuration -- then carries neither their uniform branches nor their code in its instruction stream.
-template <bool LEAN, typename Real>
+template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_domain_rand(const Params<Real>& p) {
-    if constexpr (LEAN) return false; else return p.domain_rand != 0;
+    if constexpr (LEAN == kLeanPlain) return false; else if constexpr (LEAN == kLeanDomainRand) return true; else return p.domain_rand != 0;
 }
-template <bool LEAN, typename Real>
+template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_relational(const Params<Real>& p) {
     if constexpr (LEAN) return false; else return p.relational != 0;
 }
-template <bool LEAN, typename Real>
+template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_gps(const Params<Real>& p) {
     if constexpr (LEAN) return false; else return p.gps_sigma > Real(0);
 }
-template <bool LEAN, typename Real>
+template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_wind(const Params<Real>& p) {
     if constexpr (LEAN) return false; else return p.wind_drift > 0.0;
 }
-template <bool LEAN>
+template <int LEAN>
 __device__ __forceinline__ double* feat_step_detail(const Buffers& b) {
     if constexpr (LEAN) return nullptr; else return b.step_detail;
 }
-template <bool LEAN>
+template <int LEAN>
 __device__ __forceinline__ void* feat_draw_export(const Buffers& b) {
     if constexpr (LEAN) return nullptr; else return b.draw_export;
 }
 
 // Draws of the step in flight for slot k of the tile, rebuilt at each point of use (cheap) so that nothing
 // of it stays live across the step.
-template <typename Real, bool REPLAY, int SPL, bool LEAN>
+template <typename Real, bool REPLAY, int SPL, int LEAN>
 __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
                                                                 const TileSmem<Real>& ts, int k, int e);
 
 // UAVEnvironment._execute_collect_action (uav_env.py:518-632) for one environment (slot k of the tile).
 // Results go to the tile block (and the parity diagnostics) from lane 0.
-template <typename Real, bool REPLAY, int SPL, bool LEAN>
+template <typename Real, bool REPLAY, int SPL, int LEAN>
 __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
                                                int k, int e, Sensor<Real> (&s)[SPL], Real step_loss, int lane) {
     const Draws<Real, REPLAY, SPL> dr = step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e);
@@ -1681,7 +1683,7 @@ struct RecView {  // lane-private access to record l of the swizzled tile
     }
 };
 
-template <typename Real, bool REPLAY, int SPL, bool LEAN>
+template <typename Real, bool REPLAY, int SPL, int LEAN>
 __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real>& p, const Buffers& b,
                                                                 const TileSmem<Real>& ts, int k, int e) {
     const uint64_t gid = (uint64_t)(p.env_id_offset + e);
@@ -1717,7 +1719,7 @@ __device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* acti
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
 // the environment are read from the tile block where they are used and results are written back as soon as
 // they exist, so that little besides the sensor registers is live across the phase.
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, int LEAN>
 __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffers& b, TileSmem<Real>& ts, WarpSmem& ws,
                                              int tb, int k, int e, int lane, Sensor<Real> (&s)[SPL]) {
     constexpr bool kParity = std::is_same<Real, double>::value;
@@ -1884,7 +1886,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
 #pragma unroll
     for (int q = 0; q < 2; ++q)
         if (valid[q] && collect[q])
-            collect_action<float, false, 1, true>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
+            collect_action<float, false, 1, kLeanPlain>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
                                                   step_loss[q], lane);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -1896,7 +1898,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
     }
     // ---- observation, sensor part: one Philox call for the pair (uav_env.py:638-674) ----
     {
-        const Draws<float, false, 1> dr = step_draws<float, false, 1, true>(p, b, ts, k0, base + k0);
+        const Draws<float, false, 1> dr = step_draws<float, false, 1, kLeanPlain>(p, b, ts, k0, base + k0);
         const Philox4 qp = dr.pair_call(p, lane);
         float dd[2][1], de[2][1];
         box_muller<float>(qp.x, qp.y, p.sigma, dd[0][0], de[0][0]);
@@ -1920,7 +1922,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
 
 // One launch steps every environment of the handle once.  Persistent warps: the grid covers the SMs at
 // full residency and each warp walks tiles t = warp_id, warp_id + total_warps, ...
-template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, bool LEAN = false, bool PAIR = false>
+template <typename Real, bool REPLAY, int SPL, int FPS, bool STACK, int LEAN = 0, bool PAIR = false>
 __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_blocks<Real, SPL, PAIR>())
     step_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
                 const int32_t* __restrict__ actions) {
@@ -1928,7 +1930,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    static_assert(!PAIR || (LEAN && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
+    static_assert(!PAIR || (LEAN == kLeanPlain && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
                   "the pair kernel is the plain throughput step with one sensor slot per lane");
     StepWarpSmem<Real, SPL, PAIR>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR>*>(dyn_smem)[warp];
     WarpSmem& ws = mine.ws;

@@ -83,33 +83,38 @@ template <typename Real>
 inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const int32_t* actions, bool replay,
                                  cudaStream_t st) {
     const bool two = p.P > 32;
-    // the plain UAVEnvironment step without optional features runs the LEAN instantiation (throughput build)
-    const bool lean = !std::is_same<Real, double>::value && !replay && !p.domain_rand && !p.relational &&
-                      !b.draw_export && !b.step_detail && p.fps == 3 && !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0)
+    // Throughput build, Philox, no diagnostics: the plain UAVEnvironment step and the DomainRandEnv training step run
+    // LEAN instantiations (the features they do not use are compiled out); everything else takes the generic kernel.
+    const bool lean_base = !std::is_same<Real, double>::value && !replay && !p.relational && !b.draw_export &&
+                           !b.step_detail && p.fps == 3 && !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0)
 #ifdef UAVSIM_NO_LEAN
-                      && false
+                           && false
 #endif
         ;
     if constexpr (!std::is_same<Real, double>::value) {
-        if (lean) {
+        if (lean_base) {
             const bool stack = p.frame_k > 1;
-            if (two) {
-                constexpr size_t smem = step_smem_bytes<Real, 2>();
-                constexpr int warps = step_warps<Real, 2>();
-                auto k = stack ? step_kernel<Real, false, 2, 3, true, true> : step_kernel<Real, false, 2, 3, false, true>;
-                dim3 grid;
-                Buffers bb;
-                launch_step_kernel(k, smem, warps, false, b, &grid, &bb);
-                k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);
+            dim3 grid;
+            Buffers bb;
+#define UAVSIM_LAUNCH_LEAN(S, MODE, PAIRED)                                                                   \
+    do {                                                                                                      \
+        constexpr size_t smem = step_smem_bytes<Real, S, PAIRED>();                                           \
+        constexpr int warps = step_warps<Real, S, PAIRED>();                                                  \
+        auto k = stack ? step_kernel<Real, false, S, 3, true, MODE, PAIRED> : step_kernel<Real, false, S, 3, false, MODE, PAIRED>; \
+        launch_step_kernel(k, smem, warps, PAIRED, b, &grid, &bb);                                            \
+        k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                                    \
+    } while (0)
+            if (p.domain_rand) {
+                if (two)
+                    UAVSIM_LAUNCH_LEAN(2, kLeanDomainRand, false);
+                else
+                    UAVSIM_LAUNCH_LEAN(1, kLeanDomainRand, false);
+            } else if (two) {
+                UAVSIM_LAUNCH_LEAN(2, kLeanPlain, false);
             } else {  // P <= 32: two environments per warp pass (uavsim_kernels.cuh, pair_phase)
-                constexpr size_t smem = step_smem_bytes<Real, 1, true>();
-                constexpr int warps = step_warps<Real, 1, true>();
-                auto k = stack ? step_kernel<Real, false, 1, 3, true, true, true> : step_kernel<Real, false, 1, 3, false, true, true>;
-                dim3 grid;
-                Buffers bb;
-                launch_step_kernel(k, smem, warps, true, b, &grid, &bb);
-                k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);
+                UAVSIM_LAUNCH_LEAN(1, kLeanPlain, true);
             }
+#undef UAVSIM_LAUNCH_LEAN
             return cudaGetLastError();
         }
     }

@@ -233,3 +233,25 @@ def test_lean_domain_rand_instantiation_equals_the_generic_one(pkg, max_sensors,
         assert np.array_equal(rl[k], rd[k], equal_nan=True), k
     lean.close()
     diag.close()
+
+
+@pytest.mark.parametrize("E", [1, 2, 3, 5, 17, 31])
+def test_pair_kernel_tiny_batches(pkg, E):
+    """Pair kernel with fewer environments than a tile, odd counts (an unpaired last environment) included."""
+    import torch
+    kw = dict(grid_size=(150, 150), num_sensors=20, seed=13, max_battery=6.0, precision="f32", rng="philox",
+              uav_start_position=(70.0, 80.0))
+    lean = pkg.UAVVecEnv(E, **kw)
+    diag = pkg.UAVVecEnv(E, step_detail=True, **kw)
+    lean.reset_tensors()
+    diag.reset_tensors()
+    g = torch.Generator(device=lean.device)
+    g.manual_seed(E)
+    for t in range(80):
+        a = torch.randint(0, 5, (E,), dtype=torch.int32, device=lean.device, generator=g)
+        lean.step_tensors(a)
+        diag.step_tensors(a)
+        assert torch.equal(lean.reward, diag.reward) and torch.equal(lean.obs, diag.obs) and torch.equal(lean.done, diag.done), t
+    assert int(lean.stat_sums[-1].item()) >= E
+    lean.close()
+    diag.close()

@@ -398,6 +398,13 @@ class UAVVecEnv:
         raw = self._fields[N.FIELD_ENV_RECORD].cpu().numpy()
         return raw.view(np.dtype(N.ENV_RECORD_DTYPE)).reshape(self.num_envs)
 
+    def set_battery(self, battery_wh: torch.Tensor) -> None:
+        """Overwrite `uav.battery` (Wh, float64 [E]) of every env in place -- the record column is a zero-copy view.
+        Evaluation from partial charge; bench.py uses it to desynchronise the episodes so that a timed region holds
+        truncations and in-kernel restarts at their steady-state rate instead of none."""
+        rec = self._fields[N.FIELD_ENV_RECORD].view(torch.float64)        # [E, 16]: battery is double #2 (offset 16)
+        rec[:, 2] = battery_wh.to(device=self.device, dtype=torch.float64)
+
     def generated(self) -> torch.Tensor:
         """total_data_generated per sensor [E, P] (iot_sensors.py:116)."""
         g = self._fields[N.FIELD_SENSOR_GEN]

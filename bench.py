@@ -234,6 +234,10 @@ def run_gpu_arm(args):
     n_act = 8
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
+    # Steady state instead of 1M synchronised fresh episodes: start every UAV at a random state of charge, so that
+    # truncations, terminal penalties and in-kernel restarts happen inside the timed region at the rate of a long run
+    # (a full battery lasts ~1790 random steps -- longer than the default timed region).
+    env.set_battery(5.48 + (274.0 - 5.48) * torch.rand(E, device=dev, generator=g, dtype=torch.float64))
     actions = [torch.randint(0, 5, (E,), dtype=torch.int32, device=dev, generator=g) for _ in range(n_act)]
     stream = torch.cuda.current_stream(dev)
 
@@ -350,7 +354,7 @@ def run_gpu_arm(args):
             "config": {"workload": WORKLOAD["name"], "grid": list(grid), "num_sensors": n, "envs_per_gpu": E,
                        "global_envs": E * world, "precision": "f32 state / f64 battery+returns", "rng": "philox4x32-10",
                        "actions": "uniform random, %d pre-generated device tensors cycled" % n_act,
-                       "auto_reset": True, "parallelism": "env-sharded x%d, no data-path collective" % world,
+                       "auto_reset": True, "initial_state": "random state of charge per env (episodes end inside the timed region)", "parallelism": "env-sharded x%d, no data-path collective" % world,
                        "l2": "state per launch %.2f GB >> 126 MB L2 (inputs larger than L2)" % (bpe * E / 1e9)},
             "clocks": clocks,
             "e2e": {"value": E * world * e2e_steps / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": h2d,

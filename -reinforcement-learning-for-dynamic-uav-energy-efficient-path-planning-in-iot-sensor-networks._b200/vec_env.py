@@ -198,6 +198,9 @@ class UAVVecEnv:
         self.render_mode = None
         self.metadata = {"render_modes": []}
         self._closed = False
+        self._np_host = None      # pinned staging buffers of the numpy VecEnv path (allocated on first use)
+        self._np_infos = None
+        self._np_dirty = []
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -439,18 +442,31 @@ class UAVVecEnv:
     def step_wait(self):
         if self._pending_actions is None:
             raise RuntimeError("step_wait() without step_async()")
-        self._actions_dev.copy_(self._pending_actions, non_blocking=False)
+        # one pinned staging set for the whole numpy path: actions H2D, step, obs / reward / done D2H, one sync
+        # (uavsim_step_host); the arrays handed out are fresh copies, as DummyVecEnv's are
+        if self._np_host is None:
+            self._np_host = self.make_host_buffers()
+            self._np_infos = [{} for _ in range(self.num_envs)]
+            self._np_dirty = []
+        host = self._np_host
+        host["actions"].copy_(self._pending_actions)
         self._pending_actions = None
-        self.step_tensors(self._actions_dev)
-        obs = self.obs.cpu().numpy()
-        rew = self.reward.cpu().numpy()
-        dones = self.done.cpu().numpy().astype(bool)
-        infos = [{} for _ in range(self.num_envs)]
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_step_host(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
+                                              _ptr(host["done"]), self._stream()))
+        obs = host["obs"].numpy().copy()
+        rew = host["reward"].numpy().copy()
+        dones = host["done"].numpy().astype(bool)
+        infos = self._np_infos                      # one dict per env, reused; last step's entries are cleared
+        for e in self._np_dirty:
+            infos[e] = {}
+        self._np_dirty = []
         idx = np.flatnonzero(dones)
         if idx.size:
             didx = torch.as_tensor(idx, device=self.device)
             stats = self.episode_stats[didx].cpu().numpy()
             tobs = self.terminal_obs[didx].cpu().numpy() if self.cfg.auto_reset else None
+            self._np_dirty = [int(e) for e in idx]
             for k, e in enumerate(idx):
                 st = dict(zip(N.STAT_NAMES, stats[k].tolist()))
                 info = infos[e]
@@ -459,7 +475,7 @@ class UAVVecEnv:
                     info["terminal_observation"] = tobs[k]
                     info["episode"] = {"r": st["return"], "l": int(st["length"])}   # Monitor
                     self.last_episode_stats[e] = self._episode_dict(st)
-        return obs, rew, dones, infos
+        return obs, rew, dones, list(infos)
 
     def step(self, actions):
         self.step_async(actions)

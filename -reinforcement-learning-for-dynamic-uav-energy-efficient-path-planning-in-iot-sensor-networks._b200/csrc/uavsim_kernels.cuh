@@ -1960,13 +1960,16 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
 #define UAVSIM_NEXT_BASE next_base
     int tb = 0;  // tile buffer in use
     if constexpr (kStaged) {  // prime both pipelines: records of the first tile, sensor columns of its first env
-        if (base < UAVSIM_E) {
-            tile_issue<Real>(b, actions, base, 0, lane, ts);
-            if constexpr (!PAIR) stage_issue<Real, SPL>(b, p, base, b.rec[base].num_sensors, lane, stage[0]);
-        }
+        if (base < UAVSIM_E) tile_issue<Real>(b, actions, base, 0, lane, ts);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
+        if constexpr (!PAIR) {  // the first two environments of the warp's sequence, one stage and one group each
+            if (base < UAVSIM_E) stage_issue<Real, SPL>(b, p, base, (int)ts.rec[0][0][kRN], lane, stage[0]);
+            cp_async_commit();
+            if (base + 1 < UAVSIM_E) stage_issue<Real, SPL>(b, p, base + 1, (int)ts.rec[0][1][kRN ^ 1], lane, stage[1]);
+            cp_async_commit();
+        }
         if constexpr (PAIR) {  // the first pair of the warp's sequence (sensor counts from the records just landed)
             if (base < UAVSIM_E) stage_issue<Real, SPL>(b, p, base, (int)ts.rec[0][0][kRN], lane, stage[0]);
             if (base + 1 < UAVSIM_E) stage_issue<Real, SPL>(b, p, base + 1, (int)ts.rec[0][1][kRN ^ 1], lane, stage[1]);
@@ -2105,37 +2108,47 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             const int e = base + k;
             Sensor<Real> s[SPL];
             if constexpr (kStaged) {
-                // launch the copies of the NEXT environment of this warp's sequence, then wait for the
-                // CURRENT environment's stage (issued one iteration ago)
-                // the stage buffers alternate with k: tiles hold an even number of environments (a partial
-                // tile can only be a warp's last one), so buffer k & 1 is always the one staged for slot k
-                // The NEXT tile's records + actions (T) are requested at k == 0.
-                int e1 = e + 1, n1 = 0;
-                if (k + 1 < ntile) {
-                    n1 = (int)rec[k + 1][kRN ^ (k + 1)];
-                } else {
-                    e1 = UAVSIM_NEXT_BASE;
-                    cp_async_wait<0>();  // the next tile's records (T) must have landed before they are read
-                    __syncwarp();
-                    if (e1 < UAVSIM_E) n1 = (int)ts.rec[tb ^ 1][0][kRN];
-                }
-                if (e1 < UAVSIM_E)
-                    stage_issue<Real, SPL>(b, p, e1, n1, lane, stage[(k & 1) ^ 1]);
-                cp_async_commit();
-                if (k == 0) {  // T: the other record buffer is free since the previous tile's write-back
-                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
-                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
-                    cp_async_commit();
-                }
-                if (k < 2)
-                    cp_async_wait<2>();  // commit order G(k-1), [T,] G(k): this environment's stage is G(k-1)
+                // Two stages, prefetch distance TWO environments: wait for this environment's stage (requested two
+                // iterations ago), move it to registers, and reuse the SAME stage at once for the environment two
+                // places down the warp's sequence, so a request has two full iterations to land.  Stages alternate
+                // with k: tiles hold an even number of environments (a partial tile can only be the last one).
+                // cp.async groups in commit order: G(k) = environment k + 2, plus the NEXT tile's records + actions
+                // T right after G(0); this environment's group is G(k - 2).
+                if (k == 1 || k == 2)
+                    cp_async_wait<2>();  // behind G(k-2): [G(0),] T, G(k-1)
                 else
-                    cp_async_wait<1>();
+                    cp_async_wait<1>();  // behind G(k-2): G(k-1) only -- from k == 3 on T has landed too
                 __syncwarp();
                 const bool valid = ts.flags[k] & kFlagValid;
                 if (valid)
                     load_sensors_staged<Real, SPL>(stage[k & 1], ts.N[k], lane, s);
                 __syncwarp();
+                {
+                    int e2 = e + 2, n2 = 0;
+                    bool have = false;
+                    if (k + 2 < ntile) {
+                        n2 = (int)rec[k + 2][kRN ^ (k + 2)];
+                        have = true;
+                    } else {
+                        const int r = k + 2 - ntile;  // 0 or 1: the next tile's first two environments
+                        e2 = UAVSIM_NEXT_BASE + r;
+                        if (ntile < 8) {  // a short tile has not passed the waits that retire T
+                            cp_async_wait<0>();
+                            __syncwarp();
+                        }
+                        if (e2 < UAVSIM_E) {
+                            n2 = (int)ts.rec[tb ^ 1][r][kRN ^ r];
+                            have = true;
+                        }
+                    }
+                    if (have) stage_issue<Real, SPL>(b, p, e2, n2, lane, stage[k & 1]);
+                    cp_async_commit();
+                }
+                if (k == 0) {  // T: the other record buffer is free since the previous tile's write-back
+                    if (UAVSIM_NEXT_BASE < UAVSIM_E)
+                        tile_issue<Real>(b, actions, UAVSIM_NEXT_BASE, tb ^ 1, lane, ts);
+                    cp_async_commit();
+                }
                 if (!valid) continue;
             } else {
                 if (!(ts.flags[k] & kFlagValid)) continue;

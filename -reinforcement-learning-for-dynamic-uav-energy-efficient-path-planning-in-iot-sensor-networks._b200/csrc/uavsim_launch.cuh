@@ -62,18 +62,19 @@ inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_wa
 
 // Environments per tile of a step launch: 16 when every resident warp gets at least ~2.5 tiles, else the largest
 // smaller tile that does (phases A / C run one environment per lane, so a smaller tile costs a few per cent per
-// environment but lets a small batch use the whole machine).  The pair kernel needs a multiple of 4.
-inline int choose_tile(int E, int resident_warps, bool pair) {
-    for (int t = kTile; t >= (pair ? 4 : 2); t >>= 1)
+// environment but lets a small batch use the whole machine).  The staged (float32) kernels prefetch two
+// environments / one pair ahead across tile boundaries and need a multiple of 4.
+inline int choose_tile(int E, int resident_warps, bool min4) {
+    for (int t = kTile; t >= (min4 ? 4 : 2); t >>= 1)
         if ((double)E >= 2.5 * (double)t * (double)resident_warps) return t;
-    return pair ? 4 : 2;
+    return min4 ? 4 : 2;
 }
 
 template <typename Kernel>
-inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool pair, const Buffers& b, dim3* grid, Buffers* bb) {
+inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool min4, const Buffers& b, dim3* grid, Buffers* bb) {
     const int blocks = resident_blocks(k, smem, warps);
     *bb = b;
-    bb->tile = choose_tile(b.E, blocks * warps, pair);
+    bb->tile = choose_tile(b.E, blocks * warps, min4);
     const int per_block = warps * bb->tile;
     const int need = (b.E + per_block - 1) / per_block;
     *grid = dim3((unsigned)(need < blocks ? need : blocks));
@@ -101,7 +102,7 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
         constexpr size_t smem = step_smem_bytes<Real, S, PAIRED>();                                           \
         constexpr int warps = step_warps<Real, S, PAIRED>();                                                  \
         auto k = stack ? step_kernel<Real, false, S, 3, true, MODE, PAIRED> : step_kernel<Real, false, S, 3, false, MODE, PAIRED>; \
-        launch_step_kernel(k, smem, warps, PAIRED, b, &grid, &bb);                                            \
+        launch_step_kernel(k, smem, warps, true, b, &grid, &bb);                                            \
         k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                                    \
     } while (0)
             if (p.domain_rand) {
@@ -127,7 +128,7 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
         constexpr int warps = step_warps<Real, S>();                                          \
         dim3 grid;                                                                            \
         Buffers bb;                                                                           \
-        launch_step_kernel(k, smem, warps, false, b, &grid, &bb);                             \
+        launch_step_kernel(k, smem, warps, !std::is_same<Real, double>::value, b, &grid, &bb); \
         k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                    \
     } while (0)
     if (replay) {

@@ -299,9 +299,10 @@ __device__ __forceinline__ float link_quality_of(int sf) {  // uav_env.py:647
 // sensor per step: the UAV does not move between the up-to-five draws a step makes on a sensor.
 template <typename Real>
 __device__ __forceinline__ Real det_rssi(const Params<Real>& p, float ux, float uy, float sx, float sy) {
-    const float dx = (ux - sx) * 10.0f;
-    const float dy = (uy - sy) * 10.0f;
+    float dx = ux - sx, dy = uy - sy;
     if constexpr (std::is_same<Real, double>::value) {
+        dx *= 10.0f;  // iot_sensors.py:161-162, float32
+        dy *= 10.0f;
         // reference op order in float32 (this TU is built with -fmad=false, so no contraction)
         const float g = sqrtf(dx * dx + dy * dy);
         const float d = sqrtf(g * g + p.alt2);
@@ -317,7 +318,7 @@ __device__ __forceinline__ Real det_rssi(const Params<Real>& p, float ux, float 
         return p.tx_power - pl;
     } else {
         // log10(d) = 0.5*log10(d^2): one MUFU.LG2, no square roots
-        const float d2 = fmaf(dx, dx, fmaf(dy, dy, p.alt2));
+        const float d2 = fmaf(fmaf(dx, dx, dy * dy), 100.0f, p.alt2);  // (10 dx)^2 + (10 dy)^2 + altitude^2
         const float l2 = __log2f(d2);
         const float k = 0.30102999566398120f * 0.5f;  // log10(2)/2
         return d2 < p.d_break_sq ? fmaf(-20.0f * k, l2, p.tx_power - p.c_fspl + 28.0f)
@@ -355,7 +356,10 @@ __device__ __forceinline__ Real urgency_of(const Params<Real>& p, Real buf, Real
     else
         lr = lost * fast_rcp(fmaxf(gen, 1e-30f));  // gen == 0 implies lost == 0: 0 * 1e30 = 0 without a select
     const Real u = util * (Real(1) + lr * Real(10));
-    return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
+    if constexpr (std::is_same<Real, double>::value)
+        return u < Real(0) ? Real(0) : (u > Real(1) ? Real(1) : u);
+    else
+        return __saturatef(u);  // one .SAT modifier on the producing multiply
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,15 +583,25 @@ __device__ __forceinline__ Real generated_of(const Params<Real>& p, const Sensor
 // so a sensor's mutable state is ONE 16-byte vector.  avg_rssi is a decaying average of values with
 // 4 dB of noise; an 8-ulp (6e-5 dB) rounded quantisation per step is far below anything the model
 // resolves, and NaN (= None) keeps its payload bits.  The parity layout keeps the separate u8 column.
+// None is the canonical quiet NaN 0x7fc00000 (none_value): rounding to 8 ulp maps it onto itself, so packing needs no
+// special case.
 __device__ __forceinline__ float pack_sf(float ema, int sf) {
     const uint32_t b = (__float_as_uint(ema) + 4u) & ~7u;  // round to a multiple of 8 ulp
-    const uint32_t keep = (ema != ema) ? 0x7fc00000u : b;  // canonical NaN for None
-    return __uint_as_float(keep | (uint32_t)(sf - 7));
+    return __uint_as_float(b | (uint32_t)(sf - 7));
 }
 __device__ __forceinline__ void unpack_sf(float packed, float& ema, int& sf) {
     const uint32_t b = __float_as_uint(packed);
     sf = (int)(b & 7u) + 7;
     ema = __uint_as_float(b & ~7u);
+}
+
+// avg_rssi = None
+template <typename Real>
+__device__ __forceinline__ Real none_value() {
+    if constexpr (std::is_same<Real, double>::value)
+        return CUDART_NAN;
+    else
+        return __uint_as_float(0x7fc00000u);
 }
 
 template <typename Real, int SPL>
@@ -608,7 +622,7 @@ __device__ __forceinline__ void load_sensors(const Buffers& b, const Params<Real
         // reduction, ballot and store
         SensorState<Real> v;
         v.buf = v.tx = v.lost = Real(0);
-        v.ema = Real(CUDART_NAN);
+        v.ema = none_value<Real>();
         float2 xy = make_float2(0.f, 0.f);
         Real g = Real(0);
         int sf = 12;
@@ -945,7 +959,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                 const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), episode, 1, p.key0, p.key1);
                 Real z0, z1;
                 box_muller<Real>(q.x, q.y, p.sigma, z0, z1);
-                Real ema = Real(CUDART_NAN);
+                Real ema = none_value<Real>();
                 int sf = p.init_sf;
                 adr_update(p, det0 + z0, ema, sf);
                 init_sf = sf;
@@ -1038,12 +1052,12 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
             s[k].gen = s[k].buf;
             s[k].tx = Real(0);
             s[k].lost = Real(0);
-            s[k].ema = Real(CUDART_NAN);
+            s[k].ema = none_value<Real>();
             s[k].sf = init_sf;
             if (exp) exp[UAVSIM_SLOT_U * p.P + j] = fdiv(s[k].buf, p.maxbuf);  // the fill actually used (diagnostic)
         } else {
             s[k].buf = s[k].tx = s[k].lost = s[k].gen = Real(0);
-            s[k].ema = Real(CUDART_NAN);
+            s[k].ema = none_value<Real>();
             s[k].sx = s[k].sy = 0.f;
             s[k].sf = 12;
         }
@@ -1716,6 +1730,25 @@ __device__ __forceinline__ void tile_issue(const Buffers& b, const int32_t* acti
     if (lane < n) cp_async4(&ts.action[tb][lane], actions + base + lane);
 }
 
+// IoTSensor.step (iot_sensors.py:114-125) for one sensor: the buffer grows by `nw`, is capped at max_buffer_size, and the
+// excess is lost.  Returns the excess; `over` = the cap was hit.
+template <typename Real>
+__device__ __forceinline__ Real age_buffer(const Params<Real>& p, Sensor<Real>& s, Real nw, bool& over) {
+    const Real pot = s.buf + nw;
+    Real loss;
+    if constexpr (std::is_same<Real, double>::value) {
+        over = pot > p.maxbuf;
+        loss = over ? pot - p.maxbuf : Real(0);
+        s.buf = over ? p.maxbuf : pot;
+    } else {  // min / max instead of compare + selects (pot - max is exact where it matters: pot ~ max)
+        loss = fmaxf(pot - p.maxbuf, 0.f);
+        s.buf = fminf(pot, p.maxbuf);
+        over = loss > 0.f;
+    }
+    s.lost += loss;  // + 0 when not saturated: no effect on the stored value
+    return loss;
+}
+
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
 // the environment are read from the tile block where they are used and results are written back as soon as
 // they exist, so that little besides the sensor registers is live across the phase.
@@ -1743,11 +1776,8 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
 #pragma unroll
         for (int k2 = 0; k2 < SPL; ++k2) {
             if constexpr (kParity) s[k2].gen += nw;
-            const Real pot = s[k2].buf + nw;
-            const bool over = pot > p.maxbuf;
-            loss[k2] = over ? pot - p.maxbuf : Real(0);
-            s[k2].buf = over ? p.maxbuf : pot;
-            s[k2].lost += loss[k2];  // + 0 when not saturated: no effect on the stored value
+            bool over;
+            loss[k2] = age_buffer(p, s[k2], nw, over);
             any_over |= (s[k2].active && over);
         }
         if (__any_sync(kFull, any_over)) step_loss = sensor_sum<Real, SPL>(loss, N, lane, ws.red, kSumSequential);
@@ -1867,11 +1897,8 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const float nw = p.rate * (collect[q] ? p.cd : 1.0f);
-            const float pot = s[q].buf + nw;
-            const bool over = pot > p.maxbuf;
-            loss[q] = over ? pot - p.maxbuf : 0.f;
-            s[q].buf = over ? p.maxbuf : pot;
-            s[q].lost += loss[q];
+            bool over;
+            loss[q] = age_buffer(p, s[q], nw, over);
             any_over[q] = s[q].active && over;
         }
 #pragma unroll

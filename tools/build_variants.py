@@ -36,7 +36,7 @@ def one(spec):
     info = []
     lines = (r.stdout + r.stderr).splitlines()
     for i, ln in enumerate(lines):
-        if "Compiling entry function" in ln and "step_kernelIfLb0ELi" in ln and "ELi3ELb0ELb1" in ln:
+        if "Compiling entry function" in ln and "step_kernelIfLb0ELi" in ln and "ELi3ELb0ELi1" in ln:
             info.append(ln.split("'")[1][24:44] + " | " + lines[i + 2].strip() + " | " + lines[i + 3].strip())
     obj.unlink()
     return tag, "\n".join(info)

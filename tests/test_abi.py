@@ -86,3 +86,39 @@ def test_product_package_never_imports_the_oracle():
     for f in list(PKG_DIR.glob("*.py")) + list((PKG_DIR / "csrc").glob("*")):
         txt = f.read_text()
         assert "oracle" not in txt.lower() or f.name in ("uavsim_kernels.cuh",), f
+
+
+def test_header_is_plain_c_and_links_from_c(N, tmp_path):
+    """The boundary is a C ABI: include/uavsim.h must compile as C99 and a C program must link against the shared
+    library and call its host-only entry points (no GPU needed)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_check.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "uavsim.h"
+int main(void) {
+    uavsim_config cfg;
+    uavsim_dims d;
+    if (uavsim_abi_version() != UAVSIM_ABI_VERSION) return 2;
+    if (uavsim_default_config(&cfg) != UAVSIM_OK || cfg.struct_size != sizeof(uavsim_config)) return 3;
+    cfg.num_envs = 1024; cfg.max_sensors = cfg.num_sensors = cfg.obs_slots = 50;
+    if (uavsim_query_dims(&cfg, &d) != UAVSIM_OK || d.obs_dim != 153) return 4;
+    cfg.gps_sigma = -1.0;
+    if (uavsim_query_dims(&cfg, &d) == UAVSIM_OK || strlen(uavsim_last_error()) == 0) return 5;
+    if (sizeof(uavsim_env_record) != 128) return 6;
+    printf("ok %d %lld\n", d.obs_dim, (long long)d.arena_bytes);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_check"
+    lib_dir = N.LIB_PATH.parent
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                        "-L", str(lib_dir), "-luavsim", "-Wl,-rpath," + str(lib_dir)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok 153"), (r.returncode, r.stdout, r.stderr)

@@ -2020,6 +2020,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
 
         // ---- phase A: one environment per lane ----
         const RecView R{rec[lane & (kTile - 1)], lane & (kTile - 1)};
+        bool my_valid = false;
+        int my_n = 0;
         if (lane < ntile) {
             const int e = base + lane;
             int my_flags = 0;
@@ -2082,7 +2084,12 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             }
             ts.flags[lane] = my_flags;
             ts.counts[lane] = 0;
+            my_valid = my_flags & kFlagValid;
+            my_n = R.i32(kRN);
         }
+        // one bit per environment of the tile / its sensor count in the owning lane: phase B takes them from
+        // registers (a shift, a shuffle) instead of re-reading shared memory per environment
+        const unsigned valid_mask = __ballot_sync(kFull, my_valid);
         __syncwarp();
 
         // ---- phase B (pair kernel): two environments per warp pass ----
@@ -2146,7 +2153,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 else
                     cp_async_wait<1>();  // behind G(k-2): G(k-1) only -- from k == 3 on T has landed too
                 __syncwarp();
-                const bool valid = ts.flags[k] & kFlagValid;
+                const bool valid = (valid_mask >> k) & 1u;
                 if (valid)
                     load_sensors_staged<Real, SPL>(stage[k & 1], ts.N[k], lane, s);
                 __syncwarp();
@@ -2154,7 +2161,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                     int e2 = e + 2, n2 = 0;
                     bool have = false;
                     if (k + 2 < ntile) {
-                        n2 = (int)rec[k + 2][kRN ^ (k + 2)];
+                        n2 = shfl(my_n, k + 2);
                         have = true;
                     } else {
                         const int r = k + 2 - ntile;  // 0 or 1: the next tile's first two environments
@@ -2360,7 +2367,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         // ---- tile records: shared -> global ----
 #pragma unroll
         for (int r = 0; r < kTile; ++r)
-            if (r < ntile && (ts.flags[r] & kFlagValid))
+            if ((valid_mask >> r) & 1u)
                 reinterpret_cast<uint32_t*>(b.rec + base + r)[lane] = rec[r][lane ^ r];
         if constexpr (kStaged) {
             if (ntile < 4) {  // a short (= last) tile never reached the waits that retire the record group

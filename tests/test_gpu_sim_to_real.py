@@ -130,3 +130,26 @@ def test_latency_composes_with_frame_stacking(pkg):
         assert got.shape == (E, k * od)
     plain.close()
     late.close()
+
+
+def test_host_buffer_step_returns_the_delayed_stacked_window(pkg):
+    """uavsim_step_host copies the stacked window out of the mirrored ring (2D copy): with frame stacking and
+    latency it must equal the zero-copy device view, and the numpy VecEnv.step path must return the same arrays."""
+    import torch
+    E = 300
+    env = pkg.UAVVecEnv(E, grid_size=(200, 200), num_sensors=12, seed=21, n_stack=4, latency_steps=2,
+                        uav_start_position=(100.0, 100.0), max_battery=5.0)
+    env.reset_tensors()
+    host = env.make_host_buffers()
+    g = torch.Generator()
+    g.manual_seed(3)
+    for t in range(40):
+        host["actions"].copy_(torch.randint(0, 5, (E,), dtype=torch.int32, generator=g))
+        obs, rew, done = env.step_host(host)
+        assert torch.equal(obs, env.obs.cpu()), t
+        assert torch.equal(rew, env.reward.cpu()) and torch.equal(done, env.done.cpu()), t
+    a = np.random.default_rng(0).integers(0, 5, size=E)
+    o, r, d, infos = env.step(a)
+    assert o.shape == (E, 4 * env.dims.obs_dim) and np.array_equal(o, env.obs.cpu().numpy())
+    assert np.array_equal(r, env.reward.cpu().numpy()) and len(infos) == E
+    env.close()

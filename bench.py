@@ -344,7 +344,7 @@ def run_gpu_arm(args):
             secondary = {"num_sensors": n2, "envs_per_gpu": E, "steps": k2, "ms_per_step": ms2,
                          "value_per_gpu": E / (ms2 * 1e-3), "bytes_per_env_step": bpe2,
                          "roofline_frac": bpe2 * E / (ms2 * 1e-3) / 1e9 / peak,
-                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=1, FPS=3, STACK=false, LEAN=true, PAIR=true>"}
+                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=1, FPS=3, STACK=false, LEAN=plain, PAIR=true>"}
             env2.close()
         total_steps = E * world * args.steps
         line = {
@@ -363,7 +363,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bpe,
-                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=true>" % (2 if n > 32 else 1),
+                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=plain>" % (2 if n > 32 else 1),
                          "launch_ms": launch_ms},
             "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cpu_baseline_native": cpu_c,

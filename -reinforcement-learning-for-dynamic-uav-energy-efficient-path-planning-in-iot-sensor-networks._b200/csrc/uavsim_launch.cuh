@@ -86,8 +86,9 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
     const bool two = p.P > 32;
     // Throughput build, Philox, no diagnostics: the plain UAVEnvironment step and the DomainRandEnv training step run
     // LEAN instantiations (the features they do not use are compiled out); everything else takes the generic kernel.
-    const bool lean_base = !std::is_same<Real, double>::value && !replay && !p.relational && !b.draw_export &&
-                           !b.step_detail && p.fps == 3 && !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0)
+    const bool lean_base = !std::is_same<Real, double>::value && !replay && !b.draw_export && !b.step_detail &&
+                           !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0) &&
+                           ((p.fps == 3 && !p.relational) || (p.fps == 5 && p.relational && !p.domain_rand))
 #ifdef UAVSIM_NO_LEAN
                            && false
 #endif
@@ -97,23 +98,28 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
             const bool stack = p.frame_k > 1;
             dim3 grid;
             Buffers bb;
-#define UAVSIM_LAUNCH_LEAN(S, MODE, PAIRED)                                                                   \
+#define UAVSIM_LAUNCH_LEAN(S, F, MODE, PAIRED)                                                                   \
     do {                                                                                                      \
         constexpr size_t smem = step_smem_bytes<Real, S, PAIRED>();                                           \
         constexpr int warps = step_warps<Real, S, PAIRED>();                                                  \
-        auto k = stack ? step_kernel<Real, false, S, 3, true, MODE, PAIRED> : step_kernel<Real, false, S, 3, false, MODE, PAIRED>; \
+        auto k = stack ? step_kernel<Real, false, S, F, true, MODE, PAIRED> : step_kernel<Real, false, S, F, false, MODE, PAIRED>; \
         launch_step_kernel(k, smem, warps, true, b, &grid, &bb);                                            \
         k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                                    \
     } while (0)
-            if (p.domain_rand) {
+            if (p.relational) {  // RelationalUAVEnv rows (5 features per sensor)
                 if (two)
-                    UAVSIM_LAUNCH_LEAN(2, kLeanDomainRand, false);
+                    UAVSIM_LAUNCH_LEAN(2, 5, kLeanRelational, false);
                 else
-                    UAVSIM_LAUNCH_LEAN(1, kLeanDomainRand, false);
+                    UAVSIM_LAUNCH_LEAN(1, 5, kLeanRelational, false);
+            } else if (p.domain_rand) {
+                if (two)
+                    UAVSIM_LAUNCH_LEAN(2, 3, kLeanDomainRand, false);
+                else
+                    UAVSIM_LAUNCH_LEAN(1, 3, kLeanDomainRand, false);
             } else if (two) {
-                UAVSIM_LAUNCH_LEAN(2, kLeanPlain, false);
-            } else {  // P <= 32: two environments per warp pass (uavsim_kernels.cuh, pair_phase)
-                UAVSIM_LAUNCH_LEAN(1, kLeanPlain, true);
+                UAVSIM_LAUNCH_LEAN(2, 3, kLeanPlain, false);
+            } else {  // P <= 32: two environments per warp pass (uavsim_step.cuh, pair_phase)
+                UAVSIM_LAUNCH_LEAN(1, 3, kLeanPlain, true);
             }
 #undef UAVSIM_LAUNCH_LEAN
             return cudaGetLastError();

@@ -28,18 +28,18 @@ __device__ __forceinline__ void group_argmax(Real v, int idx, Real& vmax, int& i
 template <typename Real>
 struct TileSmem;
 
-enum : int { kGeneric = 0, kLeanPlain = 1, kLeanDomainRand = 2 };
+enum : int { kGeneric = 0, kLeanPlain = 1, kLeanDomainRand = 2, kLeanRelational = 3 };
 
 // LEAN instantiations of the step kernel compile the optional features out (DomainRandEnv shaping, the
 // relational wrapper, draw export, parity diagnostics): the plain UAVEnvironment step -- the benchmarked
 // configuration -- then carries neither their uniform branches nor their code in its instruction stream.
 template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_domain_rand(const Params<Real>& p) {
-    if constexpr (LEAN == kLeanPlain) return false; else if constexpr (LEAN == kLeanDomainRand) return true; else return p.domain_rand != 0;
+    if constexpr (LEAN == kLeanDomainRand) return true; else if constexpr (LEAN != kGeneric) return false; else return p.domain_rand != 0;
 }
 template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_relational(const Params<Real>& p) {
-    if constexpr (LEAN) return false; else return p.relational != 0;
+    if constexpr (LEAN == kLeanRelational) return true; else if constexpr (LEAN != kGeneric) return false; else return p.relational != 0;
 }
 template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_gps(const Params<Real>& p) {

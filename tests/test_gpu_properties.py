@@ -255,3 +255,31 @@ def test_pair_kernel_tiny_batches(pkg, E):
     assert int(lean.stat_sums[-1].item()) >= E
     lean.close()
     diag.close()
+
+
+@pytest.mark.parametrize("N", [20, 35])
+def test_lean_relational_instantiation_equals_the_generic_one(pkg, N):
+    """RelationalUAVEnv rows (env_wrapper.py:110-313) have a LEAN instantiation too; against the generic kernel."""
+    import torch
+    E, T = 2049, 140
+    kw = dict(grid_size=(200, 200), num_sensors=N, seed=51, max_battery=10.0, relational=True, precision="f32", rng="philox",
+              uav_start_position=(90.0, 110.0))
+    lean = pkg.UAVVecEnv(E, **kw)
+    diag = pkg.UAVVecEnv(E, step_detail=True, **kw)
+    lean.reset_tensors()
+    diag.reset_tensors()
+    g = torch.Generator(device=lean.device)
+    g.manual_seed(8)
+    for t in range(T):
+        a = torch.randint(0, 5, (E,), dtype=torch.int32, device=lean.device, generator=g)
+        a = torch.where(torch.rand(E, device=lean.device, generator=g) < 0.5, torch.full_like(a, 4), a)
+        lean.step_tensors(a)
+        diag.step_tensors(a)
+        assert torch.equal(lean.reward, diag.reward), t
+        assert torch.equal(lean.obs, diag.obs), t
+    assert int(lean.stat_sums[-1].item()) > E // 2
+    rl, rd = lean.records(), diag.records()
+    for k in rl.dtype.names:
+        assert np.array_equal(rl[k], rd[k], equal_nan=True), k
+    lean.close()
+    diag.close()

@@ -263,8 +263,8 @@ struct uavsim_handle {
     Layout lay;
     char* arena = nullptr;
     bool owns_arena = false;
-    unsigned* tickets = nullptr;  // two tile-ticket counters of the step kernel (deliberately NOT in the arena: a
-                                  // snapshot / restore of the arena must not rewind them)
+    unsigned* tickets = nullptr;  // tile-ticket + finished-block counters of the step kernel (deliberately NOT in the
+                                  // arena: a snapshot / restore of the arena must not touch them)
     Params<double> p64;
     Params<float> p32;
     Buffers buf;

@@ -120,7 +120,7 @@ struct Buffers {
     uint32_t step_serial;
     int32_t frame_slot;  // row of the (2k-row mirrored ring) frame block this launch writes
     int32_t tile;        // environments per tile of this launch (2, 4, 8 or 16 <= kTile; chosen by the launcher)
-    unsigned* tile_ticket;  // two tile counters (this launch / zeroed for the next), outside the arena
+    unsigned* tile_ticket;  // [0] tiles handed out, [1] blocks finished; zeroed by the last block; outside the arena
 };
 
 // Frame stacking (VecFrameStack, dqn.py:1278; extractor layout dqn.py:612-620) without a shift pass: each

@@ -769,9 +769,10 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     // Tiles are handed out by TICKET (one atomicAdd per tile per warp, requested a whole tile ahead of its use):
     // warps that drew cheap tiles (few collect actions, few restarts) take more of them, so the launch does not end
     // on the slowest statically assigned warp, and small batches spread over the whole machine with a smaller tile.
-    // Two counters alternate between launches: this one counts, the other is zeroed for the next launch.
-    unsigned* const ticket_ctr = b.tile_ticket + (b.step_serial & 1u);
-    if (blockIdx.x == 0 && threadIdx.x == 0) b.tile_ticket[(b.step_serial & 1u) ^ 1u] = 0u;
+    // The block that finishes last zeroes the counters for the next launch (end of the kernel), so a launch carries no
+    // per-step host state besides the frame slot: with one frame per environment it can be captured in a CUDA graph
+    // and replayed (tests/test_gpu_api.py).
+    unsigned* const ticket_ctr = b.tile_ticket;
 #define UAVSIM_TAKE_TICKET() ((lane == 0) ? (int)atomicAdd(ticket_ctr, 1u) : 0)
     int base, next_base;
     {
@@ -1177,6 +1178,16 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         }
         base = next_base;
         next_base = (int)__reduce_max_sync(kFull, (unsigned)pending_ticket) * b.tile;
+    }
+    // every warp of this block has drawn its last ticket; the last block to get here resets the counters
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(b.tile_ticket + 1, 1u) == gridDim.x - 1) {
+            b.tile_ticket[0] = 0u;
+            b.tile_ticket[1] = 0u;
+            __threadfence();
+        }
     }
 #undef UAVSIM_E
 #undef UAVSIM_NEXT_BASE

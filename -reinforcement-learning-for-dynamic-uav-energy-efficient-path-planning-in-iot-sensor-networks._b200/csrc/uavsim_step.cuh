@@ -776,8 +776,8 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
 #define UAVSIM_TAKE_TICKET() ((lane == 0) ? (int)atomicAdd(ticket_ctr, 1u) : 0)
     int base, next_base;
     {
-        const int t0 = UAVSIM_TAKE_TICKET();
-        const int t1 = UAVSIM_TAKE_TICKET();
+        const int t0 = (lane == 0) ? (int)atomicAdd(ticket_ctr, 2u) : 0;  // the first two tiles in one round trip
+        const int t1 = (lane == 0) ? t0 + 1 : 0;
         // redux.sync (REDUX) delivers its result in a UNIFORM register: the compiler then knows that base, the
         // environment index, the row offsets and the loop counters derived from them are warp-uniform, keeps them
         // off the vector register file and turns the loop-control branches into uniform branches

@@ -133,6 +133,11 @@ def test_float32_throughput_build_on_replayed_draws(pkg):
     res = run_parity_case(pkg, E=2048, N=20, grid=(500, 500), steps=24, seed=53, p_collect=0.3, precision="f32")
     frac = res["discrete_mismatches"] / (res["steps"] * 20)
     assert frac < 1e-3, res
+    # per-step float quantities of the float32 build against the float64 restatement (tolerance 1e-4 relative for the
+    # state and the observation; the reward cancels large terms, 1e-3)
+    pk = res["per_key"]
+    assert pk["obs"] <= 1e-4 and pk["ema"] <= 1e-4 and pk["buf"] <= 1e-4 and pk["tx"] <= 1e-4 and pk["bytes"] <= 1e-4, pk
+    assert pk["reward"] <= 1e-3 and pk["battery"] == 0.0 and pk["lost"] <= 1e-4, pk
 
 
 def test_config2_full_episodes_to_truncation(pkg):

@@ -114,8 +114,8 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
             } else if (p.domain_rand) {
                 if (two)
                     UAVSIM_LAUNCH_LEAN(2, 3, kLeanDomainRand, false);
-                else
-                    UAVSIM_LAUNCH_LEAN(1, 3, kLeanDomainRand, false);
+                else  // P <= 32: pair kernel
+                    UAVSIM_LAUNCH_LEAN(1, 3, kLeanDomainRand, true);
             } else if (two) {
                 UAVSIM_LAUNCH_LEAN(2, 3, kLeanPlain, false);
             } else {  // P <= 32: two environments per warp pass (uavsim_step.cuh, pair_phase)

@@ -548,6 +548,37 @@ __device__ __forceinline__ Real age_buffer(const Params<Real>& p, Sensor<Real>& 
     return loss;
 }
 
+// DomainRandEnv.step shaping inputs of one environment (dqn.py:415-444): distance to the nearest sensor with data and
+// Jain's index of the per-sensor collection rates, left in the tile block for phase C.
+template <typename Real, int SPL>
+__device__ __forceinline__ void domain_rand_inputs(const Params<Real>& p, TileSmem<Real>& ts, WarpSmem& ws, int k, int N,
+                                                   int flags, int lane, Sensor<Real> (&s)[SPL]) {
+    const float cur_dist = nearest_with_data(ts.x[k], ts.y[k], s);
+    const float elapsed = ts.elapsed[k];
+    Real r1[SPL], r2[SPL];
+    int cnt = 0;
+#pragma unroll
+    for (int k2 = 0; k2 < SPL; ++k2) {
+        const Real g = generated_of(p, s[k2], elapsed);
+        const bool has = s[k2].active && g > Real(0);
+        const Real rate = has ? fdiv(s[k2].tx, g) * Real(100) : Real(0);
+        r1[k2] = rate;
+        r2[k2] = rate * rate;
+        cnt += __popc(__ballot_sync(kFull, has));
+    }
+    Real jain = Real(0);
+    if (cnt > 0) {
+        const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
+        const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
+        jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
+    }
+    if (lane == 0) {
+        ts.cur_dist[k] = cur_dist;
+        ts.jain[k] = jain;
+        if (cnt > 0) ts.flags[k] = flags | kFlagJain;
+    }
+}
+
 // Phase B for ONE environment (slot k of the tile): everything that touches the sensor columns.  Scalars of
 // the environment are read from the tile block where they are used and results are written back as soon as
 // they exist, so that little besides the sensor registers is live across the phase.
@@ -631,33 +662,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
         }
     }
 
-    // ---- DomainRandEnv.step shaping inputs (dqn.py:415-444) ----
-    if (feat_domain_rand<LEAN>(p)) {
-        const float cur_dist = nearest_with_data(ts.x[k], ts.y[k], s);
-        const float elapsed = ts.elapsed[k];
-        Real r1[SPL], r2[SPL];
-        int cnt = 0;
-#pragma unroll
-        for (int k2 = 0; k2 < SPL; ++k2) {
-            const Real g = generated_of(p, s[k2], elapsed);
-            const bool has = s[k2].active && g > Real(0);
-            const Real rate = has ? fdiv(s[k2].tx, g) * Real(100) : Real(0);
-            r1[k2] = rate;
-            r2[k2] = rate * rate;
-            cnt += __popc(__ballot_sync(kFull, has));
-        }
-        Real jain = Real(0);
-        if (cnt > 0) {
-            const Real s1 = sensor_sum<Real, SPL>(r1, N, lane, ws.red, kSumSequential);
-            const Real s2 = sensor_sum<Real, SPL>(r2, N, lane, ws.red, kSumSequential);
-            jain = s2 > Real(0) ? fdiv(s1 * s1, (Real)cnt * s2) : Real(1);
-        }
-        if (lane == 0) {
-            ts.cur_dist[k] = cur_dist;
-            ts.jain[k] = jain;
-            if (cnt > 0) ts.flags[k] = flags | kFlagJain;
-        }
-    }
+    if (feat_domain_rand<LEAN>(p)) domain_rand_inputs<Real, SPL>(p, ts, ws, k, N, flags, lane, s);
     store_sensors<Real, SPL>(b, p, e, lane, s, false);
 }
 
@@ -669,7 +674,7 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
 // counter of Draws), and the per-pass loop control is paid once per pair.  Everything per environment -- collect
 // action, reductions, stores -- runs the one-slot building blocks on a one-element view of s[q].
 // ------------------------------------------------------------------------------------------------
-template <bool STACK>
+template <bool STACK, int LEAN>
 __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers& b, TileSmem<float>& ts, WarpSmem& ws,
                                            int k0, int base, int lane, const StageBuf<float, 1>* st2, bool have_b) {
     using View = Sensor<float>(&)[1];
@@ -712,7 +717,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
 #pragma unroll
     for (int q = 0; q < 2; ++q)
         if (valid[q] && collect[q])
-            collect_action<float, false, 1, kLeanPlain>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
+            collect_action<float, false, 1, LEAN>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
                                                   step_loss[q], lane);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -724,7 +729,7 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
     }
     // ---- observation, sensor part: one Philox call for the pair (uav_env.py:638-674) ----
     {
-        const Draws<float, false, 1> dr = step_draws<float, false, 1, kLeanPlain>(p, b, ts, k0, base + k0);
+        const Draws<float, false, 1> dr = step_draws<float, false, 1, LEAN>(p, b, ts, k0, base + k0);
         const Philox4 qp = dr.pair_call(p, lane);
         float dd[2][1], de[2][1];
         box_muller<float>(qp.x, qp.y, p.sigma, dd[0][0], de[0][0]);
@@ -742,6 +747,11 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
                                                     obs_frame(p, b, base + k0 + q));
         }
     }
+    if constexpr (LEAN == kLeanDomainRand) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (valid[q]) domain_rand_inputs<float, 1>(p, ts, ws, k0 + q, N[q], flags[q], lane, reinterpret_cast<View>(s[q]));
+    }
 #pragma unroll
     for (int q = 0; q < 2; ++q) store_sensors<float, 1>(b, p, base + k0 + q, lane, reinterpret_cast<View>(s[q]), false);
 }
@@ -756,7 +766,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    static_assert(!PAIR || (LEAN == kLeanPlain && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
+    static_assert(!PAIR || ((LEAN == kLeanPlain || LEAN == kLeanDomainRand) && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
                   "the pair kernel is the plain throughput step with one sensor slot per lane");
     StepWarpSmem<Real, SPL, PAIR>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR>*>(dyn_smem)[warp];
     WarpSmem& ws = mine.ws;
@@ -934,7 +944,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 else
                     cp_async_wait<1>();  // only G(j): T has landed before the last iteration peeks at it
                 __syncwarp();
-                if constexpr (PAIR) pair_phase<STACK>(p, b, ts, ws, k, base, lane, &stage[pb * 2], k + 1 < ntile);
+                if constexpr (PAIR) pair_phase<STACK, LEAN>(p, b, ts, ws, k, base, lane, &stage[pb * 2], k + 1 < ntile);
             }
         }
         // ---- phase B: one environment per warp, sensors across lanes ----

@@ -197,7 +197,7 @@ def test_pair_kernel_with_per_env_sensor_counts(pkg):
     diag.close()
 
 
-@pytest.mark.parametrize("max_sensors,stack", [(50, 4), (32, 1)])
+@pytest.mark.parametrize("max_sensors,stack", [(50, 4), (32, 1), (32, 4), (20, 1)])
 def test_lean_domain_rand_instantiation_equals_the_generic_one(pkg, max_sensors, stack):
     """The DomainRandEnv training path (dqn.py:177-451) has its own LEAN instantiation; with parity diagnostics bound
     the generic kernel runs.  Same seed, same actions, in-kernel restarts with per-episode grids / layouts / far

@@ -23,6 +23,13 @@ NUM_ACTIONS = 5
 STAT_COUNT = 20
 STAT_SUMS = STAT_COUNT + 1
 DETAIL_COUNT = 16
+INFO_COUNT = 18
+# uavsim.h UAVSIM_INFO_*: the reference's _get_info() keys (uav_env.py:676-700) in row order; "uav_position" is
+# (x, y) and "sensor_collection_ratios" travels as its own [P] row
+INFO_NAMES = ("x", "y", "battery", "battery_percent", "sensors_collected", "current_step", "total_reward",
+              "total_data_collected", "coverage_percentage", "is_alive", "max_urgency", "avg_urgency",
+              "high_urgency_sensors", "capture_effect_triggers", "boundary_hits", "edge_steps",
+              "last_step_bytes_collected", "num_sensors")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_STATE, ERR_INVALID_ACTION, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 F64, F32 = 0, 1
@@ -75,7 +82,7 @@ class Dims(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("terminal_obs", C.c_void_p),
                 ("episode_stats", C.c_void_p), ("action_mask", C.c_void_p), ("step_detail", C.c_void_p),
-                ("draw_export", C.c_void_p)]
+                ("draw_export", C.c_void_p), ("terminal_info", C.c_void_p), ("terminal_ratios", C.c_void_p)]
 
 
 class Scenario(C.Structure):
@@ -126,6 +133,7 @@ SYMBOLS = (
     "uavsim_generate_layouts", "uavsim_set_replay", "uavsim_set_stage_grids", "uavsim_reset", "uavsim_step",
     "uavsim_step_host", "uavsim_poll_error", "uavsim_stat_sums", "uavsim_launch_count", "uavsim_frame_slot",
     "uavsim_policy_nearest_greedy", "uavsim_policy_max_throughput_greedy",
+    "uavsim_get_info", "uavsim_set_seed", "uavsim_set_frame_slot",
 )
 
 
@@ -175,7 +183,10 @@ def load() -> C.CDLL:
     lib.uavsim_policy_max_throughput_greedy.argtypes = [vp, vp, vp, vp]
     lib.uavsim_frame_slot.argtypes = [vp]
     lib.uavsim_frame_slot.restype = C.c_int
-    if lib.uavsim_abi_version() != 1:
+    lib.uavsim_get_info.argtypes = [vp, vp, vp, vp]
+    lib.uavsim_set_seed.argtypes = [vp, C.c_uint64]
+    lib.uavsim_set_frame_slot.argtypes = [vp, _i32]
+    if lib.uavsim_abi_version() != 2:
         raise ImportError("libuavsim.so ABI version mismatch")
     _lib = lib
     return lib

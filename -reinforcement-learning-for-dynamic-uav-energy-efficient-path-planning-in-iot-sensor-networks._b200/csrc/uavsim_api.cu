@@ -136,11 +136,18 @@ Params<Real> make_params(const uavsim_config& c) {
     std::memset(&p, 0, sizeof p);
     p.rate = (Real)c.data_generation_rate;
     p.maxbuf = (Real)c.max_buffer_size;
-    p.thr = (Real)c.rssi_threshold;
+    // float32 build: RSSI in dB above the range threshold (see Params::rssi_shift)
+    const double shift = std::is_same<Real, double>::value ? 0.0 : c.rssi_threshold;
+    p.rssi_shift = (Real)shift;
+    p.thr = (Real)(c.rssi_threshold - shift);
+    p.adr_t60 = (Real)(-60.0 - shift);  // iot_sensors.py:32-37
+    p.adr_t70 = (Real)(-70.0 - shift);
+    p.adr_t78 = (Real)(-78.0 - shift);
+    p.adr_t85 = (Real)(-85.0 - shift);
     p.duty_frac = (Real)(c.duty_cycle / 100.0);  // IoTSensor.duty_cycle_probability, iot_sensors.py:104-106
     p.cd = (Real)c.collection_duration;
-    p.tx_power = (Real)c.tx_power_dbm;
-    p.noise_floor = (Real)c.noise_floor_dbm;
+    p.tx_power = (Real)(c.tx_power_dbm - shift);
+    p.noise_floor = (Real)(c.noise_floor_dbm - shift);
     p.lambda = (Real)c.adr_lambda;
     p.one_minus_lambda = (Real)(1 - c.adr_lambda);
     p.sigma = (Real)c.shadowing_std_db;
@@ -149,6 +156,8 @@ Params<Real> make_params(const uavsim_config& c) {
     p.c_ht = (Real)(20 * std::log10(0.5));      // iot_sensors.py:183
     p.c_hr = (Real)(20 * std::log10(c.altitude_m));
     p.d_break = (4 * M_PI * 0.5 * c.altitude_m) / 0.345;  // iot_sensors.py:174
+    p.det_near = (float)((c.tx_power_dbm - shift) - 20 * std::log10(868.0) + 28.0);                       // :179-180
+    p.det_far = (float)((c.tx_power_dbm - shift) + 20 * std::log10(0.5) + 20 * std::log10(c.altitude_m));  // :183-185
     p.alt2 = (float)((long)c.altitude_m * (long)c.altitude_m);
     p.d_break_sq = (float)(p.d_break * p.d_break);
     p.r_per_byte = (Real)c.reward_per_byte;
@@ -269,6 +278,7 @@ struct uavsim_handle {
     Params<float> p32;
     Buffers buf;
     bool outputs_bound = false;
+    bool reseeded = false;  // uavsim_set_seed since the last reset: the next reset restarts the episode counters
     int frame_slot = -1;  // row the newest frame was written to; -1 before the first reset
     int64_t launches = 0;
     int32_t* actions_dev = nullptr;
@@ -453,6 +463,8 @@ int uavsim_bind_outputs(uavsim_handle* h, const uavsim_outputs* o, void* stream)
     b.action_mask = o->action_mask;
     b.step_detail = o->step_detail;
     b.draw_export = o->draw_export;
+    b.terminal_info = o->terminal_info;
+    b.terminal_ratios = o->terminal_ratios;
     // ghost sensor slots are written once here and never again (N is fixed per environment)
     CUDA_TRY(cudaMemsetAsync(b.obs, 0, (size_t)h->cfg.num_envs * h->dims.obs_row_floats * sizeof(float),
                              (cudaStream_t)stream));
@@ -619,8 +631,11 @@ int uavsim_reset(uavsim_handle* h, const uint8_t* mask, void* stream) {
     const int k = ring_frames(h->cfg);
     if (!mask || h->frame_slot < 0) h->frame_slot = k - 1;  // a full reset restarts the ring: window = k-1 zero frames + obs
     h->buf.frame_slot = h->frame_slot;
+    h->buf.zero_episode = h->reseeded ? 1 : 0;  // the envs this reset covers restart their episode counters
+    h->reseeded = false;
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_reset_f64(h->p64, h->buf, mask, replay, (cudaStream_t)stream)
                                                    : launch_reset_f32(h->p32, h->buf, mask, replay, (cudaStream_t)stream);
+    h->buf.zero_episode = 0;
     if (e != cudaSuccess) return cuda_fail(e, "reset_kernel launch");
     h->launches += 1;
     return UAVSIM_OK;
@@ -688,6 +703,34 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
     CUDA_TRY(cudaMemcpyAsync(reward_host, h->buf.reward, E * h->dims.real_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(done_host, h->buf.done, E, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return UAVSIM_OK;
+}
+
+int uavsim_get_info(uavsim_handle* h, double* info_dev, double* ratios_dev, void* stream) {
+    if (!h || !info_dev) return fail(UAVSIM_ERR_INVALID_ARG, "handle/info is NULL");
+    if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
+    cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_info_f64(h->p64, h->buf, info_dev, ratios_dev, (cudaStream_t)stream)
+                                                   : launch_info_f32(h->p32, h->buf, info_dev, ratios_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "info_kernel launch");
+    h->launches += 1;
+    return UAVSIM_OK;
+}
+
+int uavsim_set_seed(uavsim_handle* h, uint64_t seed) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    h->cfg.seed = seed;
+    h->p64.key0 = h->p32.key0 = (uint32_t)seed;
+    h->p64.key1 = h->p32.key1 = (uint32_t)(seed >> 32);
+    h->p64.keys = h->p32.keys = philox_key_schedule((uint32_t)seed, (uint32_t)(seed >> 32));
+    h->reseeded = true;
+    return UAVSIM_OK;
+}
+
+int uavsim_set_frame_slot(uavsim_handle* h, int32_t slot) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    if (slot < -1 || slot >= ring_frames(h->cfg)) return fail(UAVSIM_ERR_INVALID_ARG, "frame slot must be in [-1, %d)", ring_frames(h->cfg));
+    h->frame_slot = slot;
+    h->buf.frame_slot = slot;
     return UAVSIM_OK;
 }
 

@@ -60,6 +60,14 @@ struct Params {
     // iot_sensors.py / uav_env.py constants
     Real rate, maxbuf, thr, duty_frac, cd, tx_power, noise_floor, lambda, one_minus_lambda, sigma, capture_db;
     Real c_fspl, c_ht, c_hr;  // 20*log10(868), 20*log10(0.5), 20*log10(alt)
+    // ADR ladder thresholds -60 / -70 / -78 / -85 dBm (iot_sensors.py:32-37) in the build's RSSI scale.  The float32
+    // build works in dB ABOVE the range threshold (rssi - rssi_threshold: tx_power, noise_floor, thr and these four
+    // are shifted on the host, the stored avg_rssi too): the values every discrete compare looks at are then within
+    // ~30 of zero instead of near -85, so one float32 ulp is <= 1.9e-6 dB at -60 dBm, 5e-7 dB at -78 dBm and next
+    // to nothing at the range threshold itself, instead of 7.6e-6 dB everywhere.  rssi_shift = rssi_threshold there,
+    // 0 in the parity build.
+    Real adr_t60, adr_t70, adr_t78, adr_t85, rssi_shift;
+    float det_near, det_far;  // float32 build: constants of the two path-loss branches, folded in float64 on the host
     double d_break;           // (4*pi*0.5*alt)/0.345
     float alt2;               // altitude^2 as the float32 the reference adds (iot_sensors.py:167)
     float d_break_sq;         // throughput build compares squared distances
@@ -101,6 +109,8 @@ struct Buffers {
     uint8_t* action_mask;
     double* step_detail;
     void* draw_export;
+    double* terminal_info;    // [E][UAVSIM_INFO_COUNT], nullable
+    double* terminal_ratios;  // [E][P], nullable
     // replay
     const double* step_draws;
     const double* reset_draws;
@@ -118,6 +128,7 @@ struct Buffers {
     unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
     int32_t E;
     uint32_t step_serial;
+    int32_t zero_episode;  // reset launch after uavsim_set_seed: episode counters restart at 0 (a seeded reset replays)
     int32_t frame_slot;  // row of the (2k-row mirrored ring) frame block this launch writes
     int32_t tile;        // environments per tile of this launch (2, 4, 8 or 16 <= kTile; chosen by the launcher)
     unsigned* tile_ticket;  // [0] tiles handed out, [1] blocks finished; zeroed by the last block; outside the arena
@@ -321,8 +332,7 @@ __device__ __forceinline__ Real det_rssi(const Params<Real>& p, float ux, float 
         const float d2 = fmaf(fmaf(dx, dx, dy * dy), 100.0f, p.alt2);  // (10 dx)^2 + (10 dy)^2 + altitude^2
         const float l2 = __log2f(d2);
         const float k = 0.30102999566398120f * 0.5f;  // log10(2)/2
-        return d2 < p.d_break_sq ? fmaf(-20.0f * k, l2, p.tx_power - p.c_fspl + 28.0f)
-                                 : fmaf(-40.0f * k, l2, p.tx_power + p.c_ht + p.c_hr);
+        return d2 < p.d_break_sq ? fmaf(-20.0f * k, l2, p.det_near) : fmaf(-40.0f * k, l2, p.det_far);
     }
 }
 
@@ -340,10 +350,10 @@ __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Rea
     ema = (ema != ema) ? rssi : blended;  // NaN = None: the first sample initialises the average
     // the reference takes the FIRST match of the descending ladder -60 / -70 / -78 / -85 (iot_sensors.py:252-255),
     // which is the LAST assignment of the ascending one
-    sf = ema > Real(-85) ? 12 : sf;
-    sf = ema > Real(-78) ? 11 : sf;
-    sf = ema > Real(-70) ? 9 : sf;
-    sf = ema > Real(-60) ? 7 : sf;
+    sf = ema > p.adr_t85 ? 12 : sf;
+    sf = ema > p.adr_t78 ? 11 : sf;
+    sf = ema > p.adr_t70 ? 9 : sf;
+    sf = ema > p.adr_t60 ? 7 : sf;
 }
 
 // UAVEnvironment._calculate_urgency (uav_env.py:376-384)

@@ -20,4 +20,7 @@ cudaError_t launch_max_throughput_greedy_f32(const Params<float>& p, const Buffe
                                               int32_t* actions, bool replay, cudaStream_t st) {
     return launch_max_throughput_greedy_t<float>(p, b, probe_draws, actions, replay, st);
 }
+cudaError_t launch_info_f32(const Params<float>& p, const Buffers& b, double* info, double* ratios, cudaStream_t st) {
+    return launch_info_t<float>(p, b, info, ratios, st);
+}
 }  // namespace uavsim

@@ -20,4 +20,7 @@ cudaError_t launch_max_throughput_greedy_f64(const Params<double>& p, const Buff
                                               int32_t* actions, bool replay, cudaStream_t st) {
     return launch_max_throughput_greedy_t<double>(p, b, probe_draws, actions, replay, st);
 }
+cudaError_t launch_info_f64(const Params<double>& p, const Buffers& b, double* info, double* ratios, cudaStream_t st) {
+    return launch_info_t<double>(p, b, info, ratios, st);
+}
 }  // namespace uavsim

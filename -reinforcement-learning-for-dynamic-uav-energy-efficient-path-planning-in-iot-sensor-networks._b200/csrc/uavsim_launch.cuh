@@ -16,6 +16,8 @@ cudaError_t launch_step_f32(const Params<float>& p, const Buffers& b, const int3
                             cudaStream_t st);
 cudaError_t launch_reset_f32(const Params<float>& p, const Buffers& b, const uint8_t* mask, bool replay,
                              cudaStream_t st);
+cudaError_t launch_info_f64(const Params<double>& p, const Buffers& b, double* info, double* ratios, cudaStream_t st);
+cudaError_t launch_info_f32(const Params<float>& p, const Buffers& b, double* info, double* ratios, cudaStream_t st);
 cudaError_t launch_nearest_greedy_f64(const Params<double>& p, const Buffers& b, const double* probe_draws,
                                       int32_t* actions, bool replay, cudaStream_t st);
 cudaError_t launch_nearest_greedy_f32(const Params<float>& p, const Buffers& b, const double* probe_draws,
@@ -178,6 +180,18 @@ inline cudaError_t launch_reset_t(const Params<Real>& p, const Buffers& b, const
             UAVSIM_LAUNCH_RESET(false, 1);
     }
 #undef UAVSIM_LAUNCH_RESET
+    return cudaGetLastError();
+}
+
+template <typename Real>
+inline cudaError_t launch_info_t(const Params<Real>& p, const Buffers& b, double* info, double* ratios, cudaStream_t st) {
+    if (p.P > 32) {
+        auto k = info_kernel<Real, 2>;
+        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, info, ratios);
+    } else {
+        auto k = info_kernel<Real, 1>;
+        k<<<persistent_grid(k, b.E), kThreads, 0, st>>>(p, b, info, ratios);
+    }
     return cudaGetLastError();
 }
 

@@ -72,6 +72,57 @@ __device__ __forceinline__ void write_episode_stats(const Params<Real>& p, const
     }
 }
 
+// UAVEnvironment._get_info (uav_env.py:676-700) of the state in (R, s): one float64[UAVSIM_INFO_COUNT] row plus the
+// per-sensor "sensor_collection_ratios" row.  Called for the terminal state of a finished episode (the values SB3
+// callers read from infos[i], dqn.py:1148-1155, sim_to_real_sweep.py:222-225) and by the on-demand info kernel.
+// The urgency statistics follow the reference's float32 AoI array (uav_env.py:386-394): np.max, float32 np.mean
+// (pairwise sum, float32 division) and the count of entries above float32(0.8).
+template <typename Real, int SPL>
+__device__ __forceinline__ void write_info(const Params<Real>& p, int lane, const uavsim_env_record& R,
+                                           const Sensor<Real> (&s)[SPL], double* scratch, double* info, double* ratios) {
+    constexpr bool kParity = std::is_same<Real, double>::value;
+    const int N = R.num_sensors;
+    float aoi[SPL], mx = 0.f;
+    int high = 0;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        if constexpr (kParity)
+            aoi[k] = (float)(s[k].buf / p.rate);
+        else
+            aoi[k] = s[k].buf * p.inv_rate;
+        if (!s[k].active) aoi[k] = 0.f;
+        mx = fmaxf(mx, aoi[k]);  // AoI >= 0
+        high += __popc(__ballot_sync(kFull, s[k].active && aoi[k] > 0.8f));
+        if (ratios && s[k].active) {
+            const double gen = (double)generated_of(p, s[k], R.elapsed_s);
+            ratios[lane + 32 * k] = (double)s[k].tx / fmax(gen, 1e-6);
+        }
+    }
+    mx = warp_max(mx);
+    const float sum = sensor_sum<Real, SPL>(aoi, N, lane, scratch, kSumNumpy);
+    if (lane == 0 && info) {
+        const int nv = __popc(R.visited_lo) + __popc(R.visited_hi);
+        info[UAVSIM_INFO_X] = R.x;
+        info[UAVSIM_INFO_Y] = R.y;
+        info[UAVSIM_INFO_BATTERY] = R.battery;
+        info[UAVSIM_INFO_BATTERY_PERCENT] = (R.battery / p.max_battery) * 100;  // uav.py:238
+        info[UAVSIM_INFO_SENSORS_COLLECTED] = nv;
+        info[UAVSIM_INFO_CURRENT_STEP] = R.step;
+        info[UAVSIM_INFO_TOTAL_REWARD] = R.total_reward;
+        info[UAVSIM_INFO_TOTAL_DATA_COLLECTED] = R.total_data_collected;
+        info[UAVSIM_INFO_COVERAGE_PERCENTAGE] = ((double)nv / N) * 100;
+        info[UAVSIM_INFO_IS_ALIVE] = R.battery > p.batt_floor;
+        info[UAVSIM_INFO_MAX_URGENCY] = mx;
+        info[UAVSIM_INFO_AVG_URGENCY] = sum / (float)N;
+        info[UAVSIM_INFO_HIGH_URGENCY_SENSORS] = high;
+        info[UAVSIM_INFO_CAPTURE_EFFECT_TRIGGERS] = R.capture_triggers;
+        info[UAVSIM_INFO_BOUNDARY_HITS] = R.boundary_hits;
+        info[UAVSIM_INFO_EDGE_STEPS] = R.edge_steps;
+        info[UAVSIM_INFO_LAST_STEP_BYTES] = R.last_step_bytes;
+        info[UAVSIM_INFO_NUM_SENSORS] = N;
+    }
+}
+
 // Per-environment draws of the sim-to-real wrappers (sim_to_real_analysis.py:176-181, :207): GPS noise pair for
 // the observation of `step` (0 = reset observation) and, at reset, the wind angle.  REPLAY: table [E][4];
 // PHILOX: stream kStreamMisc, counter word 3 = step << 8 | 4 (words 0, 1 there are the grid / inherited-SF draws).
@@ -372,6 +423,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
     for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
         if (mask && !mask[e]) continue;
         load_record(ws, b.rec + e, lane);
+        if (b.zero_episode) {  // env.reset(seed=s): the episode that follows is a function of s alone
+            __syncwarp();
+            if (lane == 0) ws.rec.episode = 0;
+            __syncwarp();
+        }
         Sensor<Real> s[SPL];
         load_sensors<Real, SPL>(b, p, e, ws.rec.num_sensors, lane, s);
         Real* exp = b.draw_export ? reinterpret_cast<Real*>(b.draw_export) + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
@@ -384,6 +440,23 @@ __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<Real>())
         store_sensors<Real, SPL>(b, p, e, lane, s, true);
         store_record(ws, b.rec + e, lane);
         if (lane == 0 && b.done) b.done[e] = 0;
+    }
+}
+
+// _get_info() of the current state of every environment (uavsim_get_info).
+template <typename Real, int SPL>
+__global__ void __launch_bounds__(kThreads) info_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b,
+                                                        double* info, double* ratios) {
+    __shared__ WarpSmem smem[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& ws = smem[warp];
+    for (int e = blockIdx.x * kWarpsPerBlock + warp; e < b.E; e += gridDim.x * kWarpsPerBlock) {
+        load_record(ws, b.rec + e, lane);
+        Sensor<Real> s[SPL];
+        load_sensors<Real, SPL>(b, p, e, ws.rec.num_sensors, lane, s);
+        write_info<Real, SPL>(p, lane, ws.rec, s, ws.red, info + (size_t)e * UAVSIM_INFO_COUNT,
+                              ratios ? ratios + (size_t)e * p.P : nullptr);
+        __syncwarp();
     }
 }
 

@@ -245,17 +245,21 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
         urg_red = urg_red_acc;
     }
     const Real mean_urg = nwin > 0 ? fdiv(urg_acc, (Real)nwin) : Real(0);
-    // Phase 6: reward_function.py:81-128, same order of additions
-    Real reward = p.p_step + p.p_hover;
+    // Phase 6: reward_function.py:81-128, same order of additions.  The throughput build assembles it in FLOAT64
+    // from its float32 inputs: the terms reach 7e4 (100 * bytes * urgency) and can cancel down to O(1), where a
+    // float32 running sum would leave ~1e-4 of absolute rounding; the cost is a dozen DADD / DFMA per COLLECT step,
+    // identical in every lane.
+    using Acc = double;
+    Acc reward = (Acc)p.p_step + (Acc)p.p_hover;
     if (total_bytes > Real(0)) {
-        reward += p.r_per_byte * total_bytes * mean_urg;
-        if (any_new) reward += p.r_new;
+        reward += (Acc)p.r_per_byte * (Acc)total_bytes * (Acc)mean_urg;
+        if (any_new) reward += (Acc)p.r_new;
     }
-    if (urg_red > Real(0)) reward += p.r_urg_red * urg_red;
-    if (was_empty && total_bytes == Real(0)) reward += p.p_revisit;
-    reward += p.p_battery * used;
-    if (collisions > 0) reward += p.p_collision * (Real)collisions;
-    if (step_loss > Real(0)) reward += p.p_data_loss * step_loss;
+    if (urg_red > Real(0)) reward += (Acc)p.r_urg_red * (Acc)urg_red;
+    if (was_empty && total_bytes == Real(0)) reward += (Acc)p.p_revisit;
+    reward += (Acc)p.p_battery * (Acc)used;
+    if (collisions > 0) reward += (Acc)p.p_collision * (Acc)collisions;
+    if (step_loss > Real(0)) reward += (Acc)p.p_data_loss * (Acc)step_loss;
     if (N > 1) {  // calculate_starvation_penalty, reward_function.py:46-57
         Real mx = Real(0);
 #pragma unroll
@@ -274,28 +278,31 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
                     dev[k] = s[k].active ? d * d : Real(0);
                 }
                 reward += p.p_starvation * (sensor_sum<Real, SPL>(dev, N, lane, ws.red, kSumNumpy) / (Real)N);
-            } else {  // one fused shuffle tree: var = E[x^2] - E[x]^2 on x in [0, 1]
-                float s1 = 0.f, s2 = 0.f;
+            } else {  // the same two passes on shuffle trees (the one-pass E[x^2] - E[x]^2 cancels: x is in [0, 1])
+                // MUFU.RCP + one Newton step: the reciprocals scale every x (and the variance twice)
+                float inv = fast_rcp(mx), invn = fast_rcp((float)N);
+                inv = fmaf(inv, fmaf(-mx, inv, 1.0f), inv);
+                invn = fmaf(invn, fmaf(-(float)N, invn, 1.0f), invn);
+                float x[SPL], s1 = 0.f;
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) {
-                    const float v = s[k].active ? s[k].buf : 0.f;
-                    s1 += v;
-                    s2 = fmaf(v, v, s2);
+                    x[k] = s[k].active ? s[k].buf * inv : 0.f;
+                    s1 += x[k];
                 }
+                const float mean = warp_sum(s1) * invn;
+                float s2 = 0.f;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    s1 += __shfl_xor_sync(kFull, s1, o);
-                    s2 += __shfl_xor_sync(kFull, s2, o);
+                for (int k = 0; k < SPL; ++k) {
+                    const float d = x[k] - mean;
+                    s2 = s[k].active ? fmaf(d, d, s2) : s2;
                 }
-                const float inv = fast_rcp(mx), invn = fast_rcp((float)N);
-                const float mean = s1 * inv * invn;
-                reward += p.p_starvation * fmaxf(fmaf(s2 * inv * inv, invn, -mean * mean), 0.f);
+                reward += (Acc)p.p_starvation * (Acc)(warp_sum(s2) * invn);
             }
         }
     }
-    if (all_collected) reward += p.r_completion;
+    if (all_collected) reward += (Acc)p.r_completion;
     if (lane == 0) {
-        ts.creward[k] = reward;
+        ts.creward[k] = (Real)reward;
         ts.bytes[k] = total_bytes;
         ts.counts[k] = collisions | (captures << 8) | (delivered << 12);
         ts.nvis_lo[k] = h.vis_lo;
@@ -413,6 +420,9 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
     Sensor<Real> s[SPL];
     load_sensors<Real, SPL>(b, p, e, N, lane, s);
     write_episode_stats<Real, SPL>(p, b, e, lane, ws.rec, s);
+    if (b.terminal_info || b.terminal_ratios)
+        write_info<Real, SPL>(p, lane, ws.rec, s, ws.red, b.terminal_info ? b.terminal_info + (size_t)e * UAVSIM_INFO_COUNT : nullptr,
+                              b.terminal_ratios ? b.terminal_ratios + (size_t)e * p.P : nullptr);
     reset_env<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws, s, (Real*)nullptr);
     store_sensors<Real, SPL>(b, p, e, lane, s, true);
 }
@@ -1153,7 +1163,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                     d[UAVSIM_DETAIL_DATA_LOSS] = (double)step_loss;
                     d[UAVSIM_DETAIL_BASE_REWARD] = (double)reward;
                     d[UAVSIM_DETAIL_TRUNCATED] = truncated;
-                    d[14] = 0.0;
+                    d[UAVSIM_DETAIL_STARVED] = truncated ? (double)((counts >> 16) & 0xff) : 0.0;
                     d[15] = 0.0;
                 }
             }

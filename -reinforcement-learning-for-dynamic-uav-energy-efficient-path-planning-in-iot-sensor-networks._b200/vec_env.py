@@ -29,6 +29,14 @@ import torch
 from . import _native as N
 from .spaces import Box, Discrete
 
+try:  # the reference trains through stable-baselines3 (dqn.py:1276-1288): be a real VecEnv when it is importable, so
+    # that DQN._wrap_env / VecFrameStack take the batch as it is instead of re-wrapping it in a DummyVecEnv
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase  # type: ignore
+    HAVE_SB3 = True
+except Exception:  # noqa: BLE001 -- SB3 is absent from the build image: same surface, duck-typed
+    _VecEnvBase = object
+    HAVE_SB3 = False
+
 # dqn.py:63-69 -- grids per curriculum stage (sensor counts are fixed per worker)
 CURRICULUM_STAGES = [
     [(100, 100)],
@@ -49,8 +57,10 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-class UAVVecEnv:
-    """E batched UAV-LoRa environments on one GPU.
+class UAVVecEnv(_VecEnvBase):
+    """E batched UAV-LoRa environments on one GPU.  A `stable_baselines3.common.vec_env.VecEnv` subclass when SB3 is
+    importable (every abstract method of the 2.7 interface is implemented: reset, step_async, step_wait, close,
+    get_attr, set_attr, env_method, env_is_wrapped -- plus seed / step), the same surface duck-typed otherwise.
 
     Reference constructor keywords keep their names and meaning (uav_env.py:266-287):
     grid_size, sensor_positions, num_sensors, data_generation_rate, max_buffer_size,
@@ -73,7 +83,8 @@ class UAVVecEnv:
                  domain_randomisation=False, curriculum_stage=0, relational=False,
                  gps_sigma=0.0, wind_drift=0.0, latency_steps=0,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
-                 device="cuda:0", step_detail=False, export_draws=False, action_mask=True):
+                 device="cuda:0", step_detail=False, export_draws=False, action_mask=True,
+                 terminal_info: Optional[bool] = None, info_every_step=False):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope (uav_env.py:706-888)")
         if not torch.cuda.is_available():
@@ -161,9 +172,17 @@ class UAVVecEnv:
                                 if step_detail else None)
             self.draw_export = (torch.full((E, N.NUM_SLOTS, P), float("nan"), dtype=self.real_dtype, device=dev)
                                 if export_draws else None)
+            # _get_info() of the terminal state of every finished episode (what callers read from infos[i] at episode
+            # end: dqn.py:1148-1155, sim_to_real_sweep.py:222-225).  8 * (18 + P) bytes per env, so on by default only
+            # for batches a host loop can consume; the tensor API of million-env batches reads `episode_stats`.
+            if terminal_info is None:
+                terminal_info = E <= 65536
+            self.terminal_info = torch.zeros((E, N.INFO_COUNT), dtype=torch.float64, device=dev) if terminal_info else None
+            self.terminal_ratios = torch.zeros((E, P), dtype=torch.float64, device=dev) if terminal_info else None
+            self.info_every_step = bool(info_every_step)
             out = N.Outputs(_ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done), _ptr(self.terminal_obs),
                             _ptr(self.episode_stats), _ptr(self.action_mask), _ptr(self.step_detail),
-                            _ptr(self.draw_export))
+                            _ptr(self.draw_export), _ptr(self.terminal_info), _ptr(self.terminal_ratios))
             N.check(self.lib.uavsim_bind_outputs(self._h, C.byref(out), self._stream()))
             n_fields = 5 if precision == "f64" else 4      # f32: SF is packed into avg_rssi
             self._fields = {f: self._field_tensor(f) for f in range(n_fields)}
@@ -201,6 +220,10 @@ class UAVVecEnv:
         self._np_host = None      # pinned staging buffers of the numpy VecEnv path (allocated on first use)
         self._np_infos = None
         self._np_dirty = []
+        self._info_buf = None     # device rows of the on-demand _get_info kernel
+        self._next_seed = None
+        if HAVE_SB3:              # VecEnv.__init__ (sets num_envs / spaces, reset_infos, _seeds, _options, render_mode)
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -389,9 +412,11 @@ class UAVVecEnv:
         if self.precision == "f64":
             avg, sf = st[..., 3], self._fields[N.FIELD_SENSOR_SF]
         else:
+            # throughput layout: avg_rssi is stored in dB above rssi_threshold (float64 here so that undoing the
+            # shift does not round), with the spreading-factor code in its three low mantissa bits
             bits = st[..., 3].contiguous().view(torch.int32)
             sf = ((bits & 7) + 7).to(torch.uint8)
-            avg = (bits & ~7).view(torch.float32)
+            avg = (bits & ~7).view(torch.float32).double() + float(self.cfg.rssi_threshold)
         return dict(records=self._fields[N.FIELD_ENV_RECORD], buffer=st[..., 0], transmitted=st[..., 1],
                     lost=st[..., 2], avg_rssi=avg, sensor_pos=self._fields[N.FIELD_SENSOR_POS],
                     generated_base=self._fields[N.FIELD_SENSOR_GEN], spreading_factor=sf)
@@ -416,19 +441,48 @@ class UAVVecEnv:
         el = torch.as_tensor(self.records()["elapsed_s"], device=self.device)
         return g + float(self.cfg.data_generation_rate) * el[:, None]
 
-    def snapshot(self) -> torch.Tensor:
-        """Checkpoint of ALL simulation state (one device copy of the arena)."""
-        return self._arena.clone()
+    def snapshot(self) -> dict:
+        """Checkpoint of ALL simulation state: the arena (every SoA column, the records, the running statistic
+        sums), the bound observation block with its frame-ring position (with n_stack > 1 or latency_steps > 0 the
+        ring holds the k-1 (+latency) previous frames the next observations are built from) and the per-episode
+        outputs."""
+        snap = dict(arena=self._arena.clone(), obs=self._obs_buf.clone(),
+                    frame_slot=int(self.lib.uavsim_frame_slot(self._h)), reward=self.reward.clone(),
+                    done=self.done.clone(), terminal_obs=self.terminal_obs.clone(),
+                    episode_stats=self.episode_stats.clone(), last_episode_stats=list(self.last_episode_stats))
+        if self.action_mask is not None:
+            snap["action_mask"] = self.action_mask.clone()
+        if self.terminal_info is not None:
+            snap["terminal_info"], snap["terminal_ratios"] = self.terminal_info.clone(), self.terminal_ratios.clone()
+        return snap
 
-    def restore(self, snap: torch.Tensor):
-        self._arena.copy_(snap)
+    def restore(self, snap: dict):
+        self._arena.copy_(snap["arena"])
+        self._obs_buf.copy_(snap["obs"])
+        for k in ("reward", "done", "terminal_obs", "episode_stats", "action_mask", "terminal_info", "terminal_ratios"):
+            if k in snap and getattr(self, k) is not None:
+                getattr(self, k).copy_(snap[k])
+        self.last_episode_stats = list(snap["last_episode_stats"])
+        N.check(self.lib.uavsim_set_frame_slot(self._h, int(snap["frame_slot"])))
 
     # ------------------------------------------------------------------ SB3 VecEnv / Gymnasium-vector API
     def reset(self, seed=None, options=None) -> np.ndarray:
+        """`env.reset(seed=s)` (uav_env.py:400-410; the evaluation scripts reseed every episode,
+        sweep_eval.py:415,463,584): re-keys the Philox streams, then resets every env.  SB3's `seed(s)` stores the
+        seed for the next reset, as VecEnv.seed does."""
         if seed is not None:
-            self.seed(seed)
+            self._next_seed = int(seed)
+        if self._next_seed is not None:
+            self.reseed(self._next_seed)
+            self._next_seed = None
         obs = self.reset_tensors()
         return obs.cpu().numpy()
+
+    def reseed(self, seed: int) -> None:
+        """New Philox key for every later launch (uavsim_set_seed).  Draws stay a pure function of
+        (seed, global env id, episode, step, sensor, slot)."""
+        self.cfg.seed = int(seed) & (2 ** 64 - 1)
+        N.check(self.lib.uavsim_set_seed(self._h, C.c_uint64(self.cfg.seed)))
 
     def step_async(self, actions) -> None:
         a = np.asarray(actions)
@@ -461,17 +515,35 @@ class UAVVecEnv:
         for e in self._np_dirty:
             infos[e] = {}
         self._np_dirty = []
+        if self.info_every_step:                    # the reference returns _get_info() with every step (uav_env.py:488)
+            self._np_dirty = list(range(self.num_envs))
+            for e, d in enumerate(self.get_info()):
+                infos[e] = d
         idx = np.flatnonzero(dones)
         if idx.size:
             didx = torch.as_tensor(idx, device=self.device)
             stats = self.episode_stats[didx].cpu().numpy()
             tobs = self.terminal_obs[didx].cpu().numpy() if self.cfg.auto_reset else None
-            self._np_dirty = [int(e) for e in idx]
+            tinfo = tratio = None
+            if self.cfg.auto_reset and self.terminal_info is not None:
+                tinfo = self.terminal_info[didx].cpu().numpy()
+                tratio = self.terminal_ratios[didx].cpu().numpy()
+            elif not self.cfg.auto_reset and not self.info_every_step:
+                term = self.get_info(idx)           # nothing has been reset: the current state IS the terminal one
+            if not self.info_every_step:
+                self._np_dirty = [int(e) for e in idx]
             for k, e in enumerate(idx):
-                st = dict(zip(N.STAT_NAMES, stats[k].tolist()))
                 info = infos[e]
+                # infos[e] at episode end carries _get_info() of the TERMINAL state, as DummyVecEnv hands it out
+                # (the callers' keys: total_data_collected / battery / sensor_collection_ratios, dqn.py:1148-1155;
+                # coverage_percentage / total_reward / boundary_hits / edge_steps, sim_to_real_sweep.py:222-225)
+                if tinfo is not None:
+                    info.update(self._info_dict(tinfo[k], tratio[k]))
+                elif not self.cfg.auto_reset and not self.info_every_step:
+                    info.update(term[k])
                 info["TimeLimit.truncated"] = True        # terminated is never True (uav_env.py:471)
                 if tobs is not None:
+                    st = dict(zip(N.STAT_NAMES, stats[k].tolist()))
                     info["terminal_observation"] = tobs[k]
                     info["episode"] = {"r": st["return"], "l": int(st["length"])}   # Monitor
                     self.last_episode_stats[e] = self._episode_dict(st)
@@ -483,48 +555,44 @@ class UAVVecEnv:
 
     @staticmethod
     def _episode_dict(st):
-        """DomainRandEnv.last_episode_stats (dqn.py:316-331)."""
+        """DomainRandEnv.last_episode_stats (dqn.py:316-331).  `time_to_coverage` is None AS EXECUTED: the reference's
+        reset() clears `_first_full_coverage_step` (dqn.py:302) before it snapshots the statistics (:330), so its
+        dict always holds None; the step the coverage actually completed at is kept under `first_full_coverage_step`."""
         ttc = st["time_to_coverage"]
         return {"total_generated": st["total_generated"], "total_collected": st["total_collected"],
                 "total_lost": st["total_lost"], "battery_remaining": st["battery_remaining"],
                 "ndr": st["ndr"], "fairness_std": st["fairness_std"], "jains_index": st["jains_index"],
                 "grid_size": (int(st["grid_w"]), int(st["grid_h"])), "num_sensors": int(st["num_sensors"]),
                 "data_efficiency": st["data_efficiency"], "bytes_per_wh": st["bytes_per_wh"],
-                "time_to_coverage": None if ttc < 0 else int(ttc)}
+                "time_to_coverage": None, "first_full_coverage_step": None if ttc < 0 else int(ttc)}
+
+    @staticmethod
+    def _info_dict(row, ratios) -> dict:
+        """One UAVSIM_INFO_* row + ratios row -> the reference's _get_info() dict (uav_env.py:676-700)."""
+        v = dict(zip(N.INFO_NAMES, row.tolist()))
+        n = int(v.pop("num_sensors"))
+        d = {"uav_position": np.array([v.pop("x"), v.pop("y")], dtype=np.float32)}
+        for k in ("sensors_collected", "current_step", "high_urgency_sensors", "capture_effect_triggers",
+                  "boundary_hits", "edge_steps"):
+            v[k] = int(v[k])
+        v["is_alive"] = bool(v["is_alive"])
+        d.update(v)
+        d["sensor_collection_ratios"] = [float(x) for x in ratios[:n]]
+        return {k: d[k] for k in _INFO_KEYS}
 
     def get_info(self, indices=None) -> list:
-        """The reference's `_get_info()` dict (uav_env.py:676-700) for the requested envs, computed
-        on the host from one copy of the state columns."""
+        """The reference's `_get_info()` dict (uav_env.py:676-700) of the CURRENT state of the requested envs: one
+        small kernel (uavsim_get_info) fills a [E, 18] row block + the [E, P] collection ratios, one copy each."""
         idx = self._indices(indices)
-        rec = self.records()
-        st = self.state()
-        buf = st["buffer"].cpu().numpy().astype(np.float64)
-        tx = st["transmitted"].cpu().numpy().astype(np.float64)
-        gen = self.generated().cpu().numpy().astype(np.float64)
-        out = []
-        rate = float(self.cfg.data_generation_rate)
-        for e in idx:
-            r = rec[e]
-            n = int(r["num_sensors"])
-            aoi = (buf[e, :n] / rate).astype(np.float32)
-            nv = bin(int(r["visited_lo"])).count("1") + bin(int(r["visited_hi"])).count("1")
-            out.append({
-                "uav_position": np.array([r["x"], r["y"]], dtype=np.float32),
-                "battery": float(r["battery"]),
-                "battery_percent": float(r["battery"]) / float(self.cfg.max_battery) * 100,
-                "sensors_collected": nv, "current_step": int(r["step"]),
-                "total_reward": float(r["total_reward"]),
-                "total_data_collected": float(r["total_data_collected"]),
-                "coverage_percentage": nv / n * 100,
-                "is_alive": bool(r["battery"] > 0.02 * float(self.cfg.max_battery)),
-                "max_urgency": float(np.max(aoi)), "avg_urgency": float(np.mean(aoi)),
-                "high_urgency_sensors": int(np.sum(aoi > 0.8)),
-                "capture_effect_triggers": int(r["capture_triggers"]),
-                "boundary_hits": int(r["boundary_hits"]), "edge_steps": int(r["edge_steps"]),
-                "last_step_bytes_collected": float(r["last_step_bytes"]),
-                "sensor_collection_ratios": [float(tx[e, i] / max(gen[e, i], 1e-6)) for i in range(n)],
-            })
-        return out
+        if self._info_buf is None:
+            self._info_buf = (torch.zeros((self.num_envs, N.INFO_COUNT), dtype=torch.float64, device=self.device),
+                              torch.zeros((self.num_envs, self.cfg.max_sensors), dtype=torch.float64, device=self.device))
+        info, ratios = self._info_buf
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_get_info(self._h, _ptr(info), _ptr(ratios), self._stream()))
+        sel = torch.as_tensor(np.asarray(idx, dtype=np.int64), device=self.device)
+        rows, rat = info[sel].cpu().numpy(), ratios[sel].cpu().numpy()
+        return [self._info_dict(rows[k], rat[k]) for k in range(len(idx))]
 
     def _indices(self, indices):
         if indices is None:
@@ -575,9 +643,12 @@ class UAVVecEnv:
         N.check(self.lib.uavsim_set_stage_grids(self._h, len(grids), flat))
 
     def seed(self, seed: Optional[int] = None) -> Sequence[Optional[int]]:
-        """The Philox key is fixed at construction; SB3 calls seed() once before the first reset.
-        Returned values are the per-env global ids the streams are keyed on."""
-        return [int(self.cfg.env_id_offset) + i for i in range(self.num_envs)]
+        """VecEnv.seed: remembered and applied by the next `reset()` (one Philox key for the batch; env i's streams
+        are keyed on its global id, so the per-env seeds SB3 expects back are seed + global id)."""
+        if seed is None:
+            return [None for _ in range(self.num_envs)]
+        self._next_seed = int(seed)
+        return [int(seed) + int(self.cfg.env_id_offset) + i for i in range(self.num_envs)]
 
     def close(self) -> None:
         if not self._closed:

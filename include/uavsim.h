@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define UAVSIM_ABI_VERSION 1
+#define UAVSIM_ABI_VERSION 2
 #define UAVSIM_MAX_SENSORS 64 /* visited set is one 64-bit word; the reference tops out at 50 (dqn.py:121) */
 #define UAVSIM_MAX_GRIDS 8    /* grids per curriculum stage (dqn.py:63-69 uses <= 5) */
 #define UAVSIM_NUM_SLOTS 6    /* replay draw slots A,B,U,C,D,E */
@@ -156,7 +156,10 @@ typedef struct uavsim_config {
 /* State columns visible through uavsim_get_field (structure-of-arrays in HBM). */
 typedef enum uavsim_field {
     UAVSIM_FIELD_ENV_RECORD = 0,  /* [E] uavsim_env_record (128 B each) */
-    UAVSIM_FIELD_SENSOR_STATE = 1,/* [E][P][4] real: buffer, transmitted, lost, avg_rssi (NaN = None) */
+    UAVSIM_FIELD_SENSOR_STATE = 1,/* [E][P][4] real: buffer, transmitted, lost, avg_rssi (NaN = None).  F32 layout: avg_rssi is
+                                     stored as dB ABOVE config.rssi_threshold (avg_rssi - rssi_threshold, so that float32
+                                     resolves the ADR / range thresholds to <= 2e-6 dB) with the spreading-factor code
+                                     (sf - 7) in its three low mantissa bits */
     UAVSIM_FIELD_SENSOR_POS = 2,  /* [E][P][2] float32 */
     UAVSIM_FIELD_SENSOR_GEN = 3,  /* [E][P] real: F64: total_data_generated; F32: its value at reset (generated = this + rate*elapsed) */
     UAVSIM_FIELD_SENSOR_SF = 4,   /* [E][P] uint8 spreading factor 7..12 */
@@ -215,6 +218,23 @@ enum {
  * float64[UAVSIM_STAT_COUNT + 1]; element 0..COUNT-1 = sum of the stat, element COUNT = episodes finished. */
 #define UAVSIM_STAT_SUMS (UAVSIM_STAT_COUNT + 1)
 
+/* UAVEnvironment._get_info() (uav_env.py:676-700) as a float64[UAVSIM_INFO_COUNT] row; the per-sensor
+ * "sensor_collection_ratios" list travels as a separate [P] row.  Written for the TERMINAL state of a finished
+ * episode (uavsim_outputs.terminal_info / terminal_ratios: what SB3 callers read from infos[i] at episode end,
+ * dqn.py:1148-1155, sim_to_real_sweep.py:222-225) and on demand by uavsim_get_info. */
+enum {
+    UAVSIM_INFO_X = 0, UAVSIM_INFO_Y = 1,           /* "uav_position" */
+    UAVSIM_INFO_BATTERY = 2, UAVSIM_INFO_BATTERY_PERCENT = 3, UAVSIM_INFO_SENSORS_COLLECTED = 4,
+    UAVSIM_INFO_CURRENT_STEP = 5, UAVSIM_INFO_TOTAL_REWARD = 6, UAVSIM_INFO_TOTAL_DATA_COLLECTED = 7,
+    UAVSIM_INFO_COVERAGE_PERCENTAGE = 8, UAVSIM_INFO_IS_ALIVE = 9,
+    UAVSIM_INFO_MAX_URGENCY = 10, UAVSIM_INFO_AVG_URGENCY = 11, /* float32 np.max / np.mean of the AoI buf / rate */
+    UAVSIM_INFO_HIGH_URGENCY_SENSORS = 12,                      /* count of AoI > 0.8 */
+    UAVSIM_INFO_CAPTURE_EFFECT_TRIGGERS = 13, UAVSIM_INFO_BOUNDARY_HITS = 14, UAVSIM_INFO_EDGE_STEPS = 15,
+    UAVSIM_INFO_LAST_STEP_BYTES = 16,               /* kept as float32 in the record */
+    UAVSIM_INFO_NUM_SENSORS = 17,                   /* length of the ratios row (not a reference key) */
+    UAVSIM_INFO_COUNT = 18
+};
+
 /* Output buffers, allocated by the caller (e.g. torch tensors -> zero-copy), borrowed by the library.
  * reward dtype follows precision (float64 / float32).  Nullable members are optional. */
 typedef struct uavsim_outputs {
@@ -230,6 +250,10 @@ typedef struct uavsim_outputs {
     uint8_t* action_mask;  /* [E] bit a set = action a valid (derived: uav.py:175; COLLECT always), nullable */
     double* step_detail;   /* [E][UAVSIM_DETAIL_COUNT] per-step diagnostics for parity tests, nullable */
     void* draw_export;     /* [E][6][P] real: draws actually used this step (Philox mode), nullable */
+    double* terminal_info;   /* [E][UAVSIM_INFO_COUNT] _get_info() of the terminal state, written when an env finishes
+                                (auto_reset; a caller that resets by hand reads uavsim_get_info first), nullable */
+    double* terminal_ratios; /* [E][P] "sensor_collection_ratios" of the terminal state: transmitted / max(generated,
+                                1e-6) per sensor (uav_env.py:696-699), nullable */
 } uavsim_outputs;
 
 enum {
@@ -237,7 +261,9 @@ enum {
     UAVSIM_DETAIL_MEAN_URGENCY = 3, UAVSIM_DETAIL_WAS_NEW = 4, UAVSIM_DETAIL_WAS_EMPTY = 5,
     UAVSIM_DETAIL_ALL_COLLECTED = 6, UAVSIM_DETAIL_DATA_LOSS = 7, UAVSIM_DETAIL_ATTEMPT_MASK_LO = 8,
     UAVSIM_DETAIL_ATTEMPT_MASK_HI = 9, UAVSIM_DETAIL_WINNER_MASK_LO = 10, UAVSIM_DETAIL_WINNER_MASK_HI = 11,
-    UAVSIM_DETAIL_BASE_REWARD = 12, UAVSIM_DETAIL_TRUNCATED = 13, UAVSIM_DETAIL_COUNT = 16
+    UAVSIM_DETAIL_BASE_REWARD = 12, UAVSIM_DETAIL_TRUNCATED = 13,
+    UAVSIM_DETAIL_STARVED = 14, /* sensors that drew the terminal starvation penalty (reward_function.py:59-67) */
+    UAVSIM_DETAIL_COUNT = 16
 };
 
 typedef struct uavsim_dims {
@@ -333,6 +359,19 @@ int uavsim_policy_nearest_greedy(uavsim_handle* h, int32_t* actions_dev, const d
  * (:155-182).  Same argument conventions as uavsim_policy_nearest_greedy. */
 int uavsim_policy_max_throughput_greedy(uavsim_handle* h, int32_t* actions_dev, const double* probe_draws_dev,
                                         void* stream);
+
+/* ---- introspection / control ---------------------------------------------- */
+/* UAVEnvironment._get_info() of the CURRENT state of every env: info_dev [E][UAVSIM_INFO_COUNT] float64,
+ * ratios_dev [E][P] float64 (nullable).  One small kernel on `stream`. */
+int uavsim_get_info(uavsim_handle* h, double* info_dev, double* ratios_dev, void* stream);
+/* env.reset(seed=s) (uav_env.py:400-410; callers reseed per evaluation episode, sweep_eval.py:415,463,584):
+ * re-keys the Philox streams of every later launch, and the next uavsim_reset restarts the episode counters of the
+ * envs it covers at 0 -- the episode that follows is a function of (seed, global env id) alone, as a reseeded
+ * reference env replays.  Replay mode: accepted, no effect on the draws (they are injected). */
+int uavsim_set_seed(uavsim_handle* h, uint64_t seed);
+/* Restore the frame-ring position after the caller has restored the bound obs buffer from a checkpoint taken
+ * together with uavsim_frame_slot() (UAVVecEnv.snapshot / restore). */
+int uavsim_set_frame_slot(uavsim_handle* h, int32_t slot);
 
 /* ---- diagnostics ---------------------------------------------------------- */
 /* Synchronises `stream`, then reports and clears the device error word: returns

@@ -16,7 +16,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "_build" / "liboracle.so"
 MAXS = 64
 SLOTS = 6
-DETAIL_COUNT = 16
+DETAIL_COUNT = 20   # 16 shared with the CUDA detail row + 4 oracle-only (margins, reward scale)
 
 _PARAM_DOUBLES = (
     "data_generation_rate", "max_buffer_size", "rssi_threshold", "duty_cycle", "max_battery",
@@ -139,7 +139,8 @@ class COracleBatch:
         def run(a, b):
             self.lib.orc_reset_batch(C.byref(self.p), C.c_void_p(self.envs.ctypes.data), a, b,
                                      _ptr(fill, C.c_double), _ptr(draws, C.c_double), self.P,
-                                     _ptr(isf, C.c_int32), _ptr(self.obs, C.c_float), _ptr(self.mask, C.c_uint8))
+                                     _ptr(isf, C.c_int32), _ptr(self.obs, C.c_float), _ptr(self.mask, C.c_uint8),
+                                     _ptr(self.detail, C.c_double))
         if env_ids is not None:
             for e in np.asarray(env_ids).tolist():
                 run(e, e + 1)

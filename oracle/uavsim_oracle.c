@@ -75,7 +75,31 @@ typedef struct orc_env {
 
 /* per-step diagnostics (same order as UAVSIM_DETAIL_* in include/uavsim.h) */
 enum { D_COLLISIONS = 0, D_BYTES, D_URG_RED, D_MEAN_URG, D_WAS_NEW, D_WAS_EMPTY, D_ALL_COLLECTED,
-       D_DATA_LOSS, D_ATT_LO, D_ATT_HI, D_WIN_LO, D_WIN_HI, D_BASE_REWARD, D_TRUNCATED, D_COUNT = 16 };
+       D_DATA_LOSS, D_ATT_LO, D_ATT_HI, D_WIN_LO, D_WIN_HI, D_BASE_REWARD, D_TRUNCATED,
+       D_STARVED = 14, /* sensors below the collection-ratio threshold when the episode ended (reward_function.py:59-67) */
+       /* oracle-only entries (the CUDA detail row has 16 doubles): how close this env-step came to flipping one
+        * of its discrete decisions, and the scale of the reward's terms.  A float32 build is allowed to differ in
+        * a discrete decision only where the float64 margin recorded here is below its arithmetic noise
+        * (tests/parity_util.py, SURVEY.md section 7 hard part 1c). */
+       D_MARGIN_DB = 16,    /* min |lhs - rhs| over the dB compares: ADR ladder, range checks, capture threshold */
+       D_MARGIN_PROB = 17,  /* min |p_link * duty - u| over the duty-cycle gates, and |tx / gen - threshold| over the
+                               terminal starvation tests */
+       D_MARGIN_BYTES = 18, /* min |buffer + new - max_buffer| over the saturation compares and |buffer - rate * dt|
+                               over the drains (whether the buffer empties), in bytes */
+       D_REWARD_SCALE = 19, /* sum of |term| over the terms the base reward was assembled from */
+       D_COUNT = 20 };
+
+/* margin / scale accumulators of the env-step in flight (NULL = not recorded) */
+static __thread double* g_mg = NULL;
+static inline void mg_note(int slot, double lhs, double rhs) {
+    if (!g_mg) return;
+    double d = fabs(lhs - rhs);
+    if (d < g_mg[slot]) g_mg[slot] = d;
+}
+static inline double term(double v) { /* a reward term: returns v, accumulates |v| */
+    if (g_mg) g_mg[D_REWARD_SCALE] += fabs(v);
+    return v;
+}
 
 size_t orc_sizeof_env(void) { return sizeof(orc_env); }
 size_t orc_sizeof_params(void) { return sizeof(orc_params); }
@@ -171,6 +195,10 @@ static void adr_update(const orc_params* p, orc_env* e, int i, double rssi) { /*
     else
         e->ema[i] = (p->adr_lambda * rssi) + ((1 - p->adr_lambda) * e->ema[i]);
     double avg = e->ema[i];
+    mg_note(D_MARGIN_DB, avg, -60);
+    mg_note(D_MARGIN_DB, avg, -70);
+    mg_note(D_MARGIN_DB, avg, -78);
+    mg_note(D_MARGIN_DB, avg, -85);
     if (avg > -60)
         e->sf[i] = 7;
     else if (avg > -70)
@@ -208,6 +236,7 @@ static void observe(const orc_params* p, orc_env* e, const double* draws, int P,
         double det = det_rssi(p, e->x, e->y, e->spx[i], e->spy[i]);
         adr_update(p, e, i, det + draws[SLOT_D * P + i]);
         double r_e = det + draws[SLOT_E * P + i];
+        mg_note(D_MARGIN_DB, r_e, p->rssi_threshold);
         double lq = r_e >= p->rssi_threshold ? link_quality(e->sf[i]) : 0.0;
         float* o = obs + 3 + fps * i;
         o[0] = (float)(e->buf[i] / p->max_buffer_size);
@@ -346,10 +375,10 @@ static double move_action(const orc_params* p, orc_env* e, int a, double step_lo
         e->boundary_hits++;
     }
     double used = before - e->battery;
-    double r = p->penalty_step; /* reward_function.py:69-79 */
-    r += ok ? p->reward_movement : p->penalty_boundary;
-    r += p->penalty_battery * used;
-    r += p->penalty_data_loss * step_loss; /* uav_env.py:514 */
+    double r = term(p->penalty_step); /* reward_function.py:69-79 */
+    r += term(ok ? p->reward_movement : p->penalty_boundary);
+    r += term(p->penalty_battery * used);
+    r += term(p->penalty_data_loss * step_loss); /* uav_env.py:514 */
     return r;
 }
 
@@ -370,6 +399,7 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
         if (e->buf[i] <= 0) continue;
         adr_update(p, e, i, det[i] + draws[SLOT_A * P + i]);
         double rb = det[i] + draws[SLOT_B * P + i];
+        mg_note(D_MARGIN_DB, rb, thr);
         double pl;
         if (rb < thr)
             pl = 0.0;
@@ -378,6 +408,7 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
             pl = 1.0 / (1.0 + exp(-(snr - required_snr(e->sf[i]))));
         }
         double pall = pl * (p->duty_cycle / 100.0);
+        mg_note(D_MARGIN_PROB, pall, draws[SLOT_U * P + i]);
         if (pall > draws[SLOT_U * P + i]) {
             attempt[i] = 1;
             att_mask |= 1ull << i;
@@ -409,6 +440,7 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
             winners[nwin++] = a;
         } else {
             collisions += k - 1;
+            mg_note(D_MARGIN_DB, e->cur[a], e->cur[b] + p->capture_threshold_db);
             if (e->cur[a] > (e->cur[b] + p->capture_threshold_db)) {
                 winners[nwin++] = a;
                 e->capture_triggers++;
@@ -421,10 +453,12 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
         int i = winners[w];
         win_mask |= 1ull << i;
         double rc = det[i] + draws[SLOT_C * P + i];
+        mg_note(D_MARGIN_DB, rc, thr);
         int in_range = rc >= thr;
         double got = 0.0;
         if (in_range && e->buf[i] > 0) {
             double cap = data_rate(e->sf[i]) * cd;
+            mg_note(D_MARGIN_BYTES, e->buf[i], cap);
             got = e->buf[i] < cap ? e->buf[i] : cap;
             e->buf[i] -= got;
             e->tx[i] += got;
@@ -457,16 +491,16 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
         for (int w = 0; w < nwin; w++) u[w] = urgency(p, e, winners[w]);
         mean_urg = np_sum_f64(u, nwin) / nwin;
     }
-    double r = p->penalty_step + p->penalty_hover; /* reward_function.py:81-128 */
+    double r = term(p->penalty_step + p->penalty_hover); /* reward_function.py:81-128 */
     if (total > 0) {
-        r += p->reward_per_byte * total * mean_urg;
-        if (any_new) r += p->reward_new_sensor;
+        r += term(p->reward_per_byte * total * mean_urg);
+        if (any_new) r += term(p->reward_new_sensor);
     }
-    if (urg_red > 0) r += p->reward_urgency_reduction * urg_red;
-    if (was_empty && total == 0) r += p->penalty_revisit;
-    r += p->penalty_battery * used;
-    if (collisions > 0) r += p->penalty_collision * collisions;
-    if (step_loss > 0) r += p->penalty_data_loss * step_loss;
+    if (urg_red > 0) r += term(p->reward_urgency_reduction * urg_red);
+    if (was_empty && total == 0) r += term(p->penalty_revisit);
+    r += term(p->penalty_battery * used);
+    if (collisions > 0) r += term(p->penalty_collision * collisions);
+    if (step_loss > 0) r += term(p->penalty_data_loss * step_loss);
     if (N > 1) { /* reward_function.py:46-57 */
         double mx = e->buf[0];
         for (int i = 1; i < N; i++) mx = e->buf[i] > mx ? e->buf[i] : mx;
@@ -478,10 +512,10 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
                 double d = nrm[i] - mean;
                 dev[i] = d * d;
             }
-            r += p->penalty_starvation * (np_sum_f64(dev, N) / N);
+            r += term(p->penalty_starvation * (np_sum_f64(dev, N) / N));
         }
     }
-    if (all_collected) r += p->reward_completion;
+    if (all_collected) r += term(p->reward_completion);
     e->collisions += collisions;
     if (detail) {
         detail[D_COLLISIONS] = collisions;
@@ -506,8 +540,11 @@ static double collect_action(const orc_params* p, orc_env* e, const double* draw
 int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draws, const double* dwell, int P,
                  float* obs, double* reward_out, uint8_t* mask, double* detail) {
     if (action < 0 || action > 4) return -1;
-    if (detail)
+    if (detail) {
         for (int k = 0; k < D_COUNT; k++) detail[k] = 0.0;
+        detail[D_MARGIN_DB] = detail[D_MARGIN_PROB] = detail[D_MARGIN_BYTES] = INFINITY;
+    }
+    g_mg = detail;
     double prev_dist = e->prev_dist_nearest;
     e->step += 1;
     double W = (double)e->W, H = (double)e->H, ux = (double)e->x, uy = (double)e->y, eps = 1e-6;
@@ -518,6 +555,7 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
         double nw = p->data_generation_rate * dt;
         e->gen[i] += nw;
         double pot = e->buf[i] + nw;
+        mg_note(D_MARGIN_BYTES, pot, p->max_buffer_size);
         if (pot > p->max_buffer_size) {
             double loss = pot - p->max_buffer_size;
             e->buf[i] = p->max_buffer_size;
@@ -540,18 +578,25 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
     if (truncated) { /* uav_env.py:481-485, reward_function.py:59-67 */
         int unvisited = 0;
         for (int i = 0; i < e->N; i++) unvisited += !e->visited[i];
-        if (unvisited > 0) r += p->penalty_unvisited * unvisited;
+        if (unvisited > 0) r += term(p->penalty_unvisited * unvisited);
         double pen = 0.0;
-        for (int i = 0; i < e->N; i++)
-            if (e->gen[i] > 0 && e->tx[i] / e->gen[i] < p->starvation_cr_threshold) pen += p->penalty_starved;
-        r += pen;
+        int starved = 0;
+        for (int i = 0; i < e->N; i++) {
+            if (e->gen[i] > 0) mg_note(D_MARGIN_PROB, e->tx[i] / e->gen[i], p->starvation_cr_threshold);
+            if (e->gen[i] > 0 && e->tx[i] / e->gen[i] < p->starvation_cr_threshold) {
+                pen += p->penalty_starved;
+                starved++;
+            }
+        }
+        r += term(pen);
+        if (detail) detail[D_STARVED] = starved;
     }
     e->total_reward += r;
     observe(p, e, draws, P, obs);
     double shaped = r;
     if (p->domain_rand) { /* dqn.py:415-444 */
         double cur = dist_nearest_with_data(e);
-        if (prev_dist > 0) shaped += p->prox_eta * (prev_dist - cur);
+        if (prev_dist > 0) shaped += term(p->prox_eta * (prev_dist - cur));
         e->prev_dist_nearest = cur;
         int nv = 0;
         for (int i = 0; i < e->N; i++) nv += e->visited[i];
@@ -568,7 +613,7 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
         }
         if (cnt > 0) {
             double j = (cnt > 0 && s2 > 0) ? (s1 * s1) / (cnt * s2) : 1.0;
-            shaped += p->jain_bonus * (j - 0.5) / e->N;
+            shaped += term(p->jain_bonus * (j - 0.5) / e->N);
         }
     }
     if (p->relational) { /* env_wrapper.py:169-198 */
@@ -605,17 +650,25 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
         detail[D_BASE_REWARD] = r;
         detail[D_TRUNCATED] = truncated;
     }
+    g_mg = NULL;
     return truncated;
 }
 
 /* Batched drivers over the env range [e0, e1): callers parallelise by giving disjoint ranges to
  * host threads (ctypes releases the GIL).  draws: [E][6][P]; fill: [E][P]; obs: [E][obs_dim]. */
 void orc_reset_batch(const orc_params* p, orc_env* envs, int e0, int e1, const double* fill,
-                     const double* draws, int P, const int32_t* init_sf, float* obs, uint8_t* mask) {
+                     const double* draws, int P, const int32_t* init_sf, float* obs, uint8_t* mask,
+                     double* detail /* nullable [E][D_COUNT]: only the margin entries are written */) {
     int dim = 3 + p->features_per_sensor * p->obs_slots;
-    for (int e = e0; e < e1; e++)
+    for (int e = e0; e < e1; e++) {
+        if (detail) {
+            g_mg = detail + (size_t)e * D_COUNT;
+            g_mg[D_MARGIN_DB] = g_mg[D_MARGIN_PROB] = g_mg[D_MARGIN_BYTES] = INFINITY;
+        }
         orc_reset_env(p, &envs[e], fill ? fill + (size_t)e * P : NULL, draws + (size_t)e * ORC_SLOTS * P, P,
                       init_sf ? init_sf[e] : 0, obs + (size_t)e * dim, mask ? mask + e : NULL);
+        g_mg = NULL;
+    }
 }
 
 /* Returns the number of invalid actions. */

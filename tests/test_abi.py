@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(N):
     lib = N.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.uavsim_abi_version() == 1
+    assert lib.uavsim_abi_version() == 2
 
 
 def test_struct_sizes_match_header(N):

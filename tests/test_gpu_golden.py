@@ -62,10 +62,28 @@ def test_cuda_reproduces_reference_golden(pkg, name, seeds, _):
         rec = env.records()
         sf = env.state()["spreading_factor"].cpu().numpy()
         det = env.step_detail.cpu().numpy()
+        infos = env.get_info()                                   # _get_info() through the device kernel, every step
         for k, (g, first, S, oenv) in enumerate(eps):
             if t >= lens[k]:
                 continue
             tag = (name, seeds[k], t)
+            # UAVEnvironment._get_info (uav_env.py:676-700) against the values the reference's own info dicts held
+            inf = infos[k]
+            assert inf["high_urgency_sensors"] == g["i_high_urgency_sensors"][t], tag
+            assert inf["sensors_collected"] == g["i_sensors_collected"][t], tag
+            assert inf["current_step"] == t + 1 and inf["boundary_hits"] == g["boundary_hits"][t], tag
+            assert inf["edge_steps"] == g["edge_steps"][t] and inf["capture_effect_triggers"] == g["capture_triggers"][t], tag
+            assert abs(inf["last_step_bytes_collected"] - g["last_step_bytes"][t]) <= 1e-6 * max(1.0, g["last_step_bytes"][t]), tag
+            sp = np.flatnonzero(g["sparse_idx"] == t)
+            if sp.size:
+                j = int(sp[0])
+                assert np.array_equal(np.asarray(inf["sensor_collection_ratios"]), g["sp_i_ratios"][j]), tag
+                assert inf["max_urgency"] == g["sp_i_max_urgency"][j] and inf["avg_urgency"] == g["sp_i_avg_urgency"][j], tag
+                assert inf["coverage_percentage"] == g["sp_i_coverage_percentage"][j], tag
+                for a, b in ((inf["total_reward"], g["sp_total_reward"][j]), (inf["battery_percent"], g["sp_i_battery_percent"][j]),
+                             (inf["total_data_collected"], g["sp_total_data_collected"][j])):
+                    assert abs(a - b) <= 1e-9 * max(abs(a), abs(b), 1e-300), (tag, a, b)
+                assert inf["is_alive"] == (g["battery"][t] > 0.02 * env.cfg.max_battery), tag
             # discrete: bit-exact against the REFERENCE's recorded values
             assert bool(done[k]) == bool(g["truncated"][t]), tag
             assert rec["x"][k] == g["pos"][t][0] and rec["y"][k] == g["pos"][t][1], tag

@@ -126,18 +126,64 @@ def test_single_sensor_and_single_env_edge_cases(pkg):
     _check(run_parity_case(pkg, E=9, N=33, grid=(10, 10), steps=60, seed=47, p_collect=0.3))
 
 
-def test_float32_throughput_build_on_replayed_draws(pkg):
-    """The float32 build on the same draws: floats within the 1e-4 bar wherever no discrete decision
-    flipped; flips are rare and counted (float32 state cannot promise bit-exact thresholds)."""
+# ---- the float32 throughput build (what bench.py times) against the float64 oracle ----------------------------
+# BASELINE.json: discrete state bit-exact, floats within 1e-4 relative of the reference's float64.  A float32 state
+# cannot promise bit-exact thresholds: a discrete difference is accepted ONLY where the float64 oracle's own margin
+# at that compare is below the float32 arithmetic noise (parity_util.F32_MARGIN; SURVEY.md section 7 hard part 1c),
+# the count is printed, and the diverged environment leaves the comparison.  Floats: 1e-4 relative to
+# max(|value|, 1 % of the quantity's full scale); the reward relative to the sum of |term| it is assembled from
+# (its terms reach 7e4 and cancel; the reference's own reward carries ~3e-4 of ABSOLUTE float32 noise through the
+# float32 AoI differences of uav_env.py:599-602, so no non-bit-exact implementation can do better in absolute terms)
+# and, where at least half of the term mass survives (|r| >= scale / 2), plainly relative to |r|.
+F32_CASES = {
+    # the benchmarked shape: N = 50, two sensor slots per lane; "philox" also runs the LEAN twin (= the timed kernel)
+    "n50_replay": dict(E=1024, steps=32, N=50, grid=(1000, 1000), p_collect=0.3, start="random"),
+    "n50_philox_lean": dict(E=1024, steps=32, N=50, grid=(1000, 1000), p_collect=0.3, start="random", draws="philox",
+                            lean_twin=True),
+    "n50_collect98": dict(E=1024, steps=24, N=50, grid=(300, 300), p_collect=0.98, start=(150.0, 150.0),
+                          draws="philox", lean_twin=True),
+    # N = 20: one slot per lane; the LEAN twin is the PAIR kernel (bench.py's secondary)
+    "n20_replay": dict(E=2048, steps=32, N=20, grid=(500, 500), p_collect=0.3),
+    "n20_philox_pair": dict(E=2048, steps=32, N=20, grid=(500, 500), p_collect=0.3, draws="philox", lean_twin=True),
+    "n20_collect98": dict(E=2048, steps=32, N=20, grid=(200, 200), p_collect=0.98, start=(100.0, 100.0),
+                          draws="philox", lean_twin=True),
+    # DomainRandEnv: Philox scenario (grid / layout / far start / inherited SF drawn in-kernel), and replayed
+    # scenarios with in-kernel restarts + terminal penalties
+    "dr_n20_philox": dict(E=2048, steps=32, N=20, P=20, grid=(300, 300), p_collect=0.4, start="random",
+                          domain_rand=True, obs_slots=50, draws="philox", lean_twin=True),
+    "dr_n40_replay_restarts": dict(E=1024, steps=40, N=40, P=40, grid=(300, 300), p_collect=0.4, start="random",
+                                   domain_rand=True, obs_slots=50, auto_reset=True,
+                                   params_over=dict(max_battery=6.0), ref_kwargs=dict(max_battery=6.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(F32_CASES))
+def test_float32_throughput_build_against_the_oracle(pkg, name):
     from parity_util import run_parity_case
-    res = run_parity_case(pkg, E=2048, N=20, grid=(500, 500), steps=24, seed=53, p_collect=0.3, precision="f32")
-    frac = res["discrete_mismatches"] / (res["steps"] * 20)
-    assert frac < 1e-3, res
-    # per-step float quantities of the float32 build against the float64 restatement (tolerance 1e-4 relative for the
-    # state and the observation; the reward cancels large terms, 1e-3)
+    kw = dict(F32_CASES[name])
+    n = kw["N"]
+    res = run_parity_case(pkg, seed=53, precision="f32", margin_aware=True, **kw)
+    sensor_steps = res["steps"] * n
+    print("\n[f32 parity] %s: %d sensor-steps, %d justified flips (margins %s), per-key %s, reward/scale %.2e, "
+          "reward rel (uncancelled, %d of %d) %.2e" %
+          (name, sensor_steps, res["flips"], [m[2] for m in res["flip_margins"]],
+           {k: "%.1e" % v for k, v in res["per_key"].items()}, res["reward_abs_over_scale"],
+           res.get("rewards_uncancelled", 0), res.get("rewards_compared", 0), res.get("reward_rel_uncancelled", 0.0)))
+    assert sensor_steps >= 10 ** 6
+    assert res["unmargined_flips"] == 0, res                 # every discrete difference is a justified flip
+    assert res["discrete_mismatches"] == 0, res
+    assert res["flips"] <= max(4, 4e-6 * sensor_steps), res  # and they are rare: ~0.5 per million sensor-steps measured
     pk = res["per_key"]
-    assert pk["obs"] <= 1e-4 and pk["ema"] <= 1e-4 and pk["buf"] <= 1e-4 and pk["tx"] <= 1e-4 and pk["bytes"] <= 1e-4, pk
-    assert pk["reward"] <= 1e-3 and pk["battery"] == 0.0 and pk["lost"] <= 1e-4, pk
+    assert pk["battery"] == 0.0, pk                          # float64 in both builds
+    for k in ("obs", "ema", "buf", "tx", "lost", "gen", "bytes", "urgency_reduced", "mean_urgency", "data_loss",
+              "total_data_collected", "total_reward", "episode_return", "reward", "base_reward"):
+        assert pk[k] <= FLOAT_TOL, (k, pk)
+    assert res["reward_abs_over_scale"] <= FLOAT_TOL, res
+    assert res.get("reward_rel_uncancelled", 0.0) <= FLOAT_TOL and res["rewards_uncancelled"] > 0.5 * res["rewards_compared"], res
+    if kw.get("lean_twin"):
+        assert res["lean_twin_steps"] == kw["steps"]
+    if kw.get("auto_reset"):
+        assert res["dones"] >= kw["E"], res
 
 
 def test_config2_full_episodes_to_truncation(pkg):

@@ -96,10 +96,10 @@ def test_snapshot_restore_round_trip(pkg):
     _run(env, 20, seed=3)
     snap = env.snapshot()
     _run(env, 25, seed=4)
-    a = (env.obs.clone(), env.reward.clone(), env.done.clone(), env.snapshot())
+    a = (env.obs.clone(), env.reward.clone(), env.done.clone(), env.snapshot()["arena"])
     env.restore(snap)
     _run(env, 25, seed=4)
-    b = (env.obs, env.reward, env.done, env.snapshot())
+    b = (env.obs, env.reward, env.done, env.snapshot()["arena"])
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     env.close()

@@ -133,7 +133,7 @@ SYMBOLS = (
     "uavsim_generate_layouts", "uavsim_set_replay", "uavsim_set_stage_grids", "uavsim_reset", "uavsim_step",
     "uavsim_step_host", "uavsim_poll_error", "uavsim_stat_sums", "uavsim_launch_count", "uavsim_frame_slot",
     "uavsim_policy_nearest_greedy", "uavsim_policy_max_throughput_greedy",
-    "uavsim_get_info", "uavsim_set_seed", "uavsim_set_frame_slot",
+    "uavsim_get_info", "uavsim_set_seed", "uavsim_set_frame_slot", "uavsim_set_host_chunks",
 )
 
 
@@ -186,6 +186,7 @@ def load() -> C.CDLL:
     lib.uavsim_get_info.argtypes = [vp, vp, vp, vp]
     lib.uavsim_set_seed.argtypes = [vp, C.c_uint64]
     lib.uavsim_set_frame_slot.argtypes = [vp, _i32]
+    lib.uavsim_set_host_chunks.argtypes = [vp, _i32]
     if lib.uavsim_abi_version() != 2:
         raise ImportError("libuavsim.so ABI version mismatch")
     _lib = lib

@@ -282,6 +282,10 @@ struct uavsim_handle {
     int frame_slot = -1;  // row the newest frame was written to; -1 before the first reset
     int64_t launches = 0;
     int32_t* actions_dev = nullptr;
+    // uavsim_step_host pipeline: the copy-out of env range k runs on `copy_stream` while range k+1 is stepped
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_range[8] = {}, ev_copied = nullptr;
+    int host_chunks = 4;
 };
 
 extern "C" {
@@ -445,6 +449,10 @@ int uavsim_create(const uavsim_config* c, void* arena_dev, size_t arena_bytes, v
 
 int uavsim_destroy(uavsim_handle* h) {
     if (!h) return UAVSIM_OK;
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t& ev : h->ev_range)
+        if (ev) cudaEventDestroy(ev);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->owns_arena) cudaFree(h->arena);
     cudaFree(h->tickets);
     delete h;
@@ -641,6 +649,55 @@ int uavsim_reset(uavsim_handle* h, const uint8_t* mask, void* stream) {
     return UAVSIM_OK;
 }
 
+// The buffers of the env range [e0, e0 + n): every per-env pointer advanced by e0.  Environments are independent and
+// their Philox streams are keyed by the GLOBAL env id (env_id_offset + e0 here), so stepping a batch as several ranges is
+// bit-identical to stepping it in one launch (tests/test_gpu_api.py).
+static Buffers range_buffers(const uavsim_handle* h, int e0, int n) {
+    Buffers b = h->buf;
+    const size_t P = (size_t)h->cfg.max_sensors, rb = (size_t)h->dims.real_bytes, k = (size_t)e0;
+    b.E = n;
+    b.rec += k;
+    b.sstate = (char*)b.sstate + k * P * 4 * rb;
+    b.spos += k * P;
+    b.sgen = (char*)b.sgen + k * P * rb;
+    b.ssf += k * P;
+    b.obs += k * (size_t)h->dims.obs_row_floats;
+    b.reward = (char*)b.reward + k * rb;
+    b.done += k;
+    if (b.terminal_obs) b.terminal_obs += k * (size_t)h->cfg.frame_stack * (size_t)h->dims.obs_dim;
+    if (b.episode_stats) b.episode_stats += k * UAVSIM_STAT_COUNT;
+    if (b.action_mask) b.action_mask += k;
+    if (b.step_detail) b.step_detail += k * UAVSIM_DETAIL_COUNT;
+    if (b.draw_export) b.draw_export = (char*)b.draw_export + k * UAVSIM_NUM_SLOTS * P * rb;
+    if (b.terminal_info) b.terminal_info += k * UAVSIM_INFO_COUNT;
+    if (b.terminal_ratios) b.terminal_ratios += k * P;
+    if (b.step_draws) b.step_draws += k * UAVSIM_NUM_SLOTS * P;
+    if (b.reset_draws) b.reset_draws += k * UAVSIM_NUM_SLOTS * P;
+    if (b.reset_fill) b.reset_fill += k * P;
+    if (b.reset_init_sf) b.reset_init_sf += k;
+    if (b.rs_sensor_xy) b.rs_sensor_xy += k * P * 2;
+    if (b.rs_num_sensors) b.rs_num_sensors += k;
+    if (b.rs_grid_wh) b.rs_grid_wh += k * 2;
+    if (b.rs_start_xy) b.rs_start_xy += k * 2;
+    if (b.dwell_draws) b.dwell_draws += k * P;
+    if (b.step_env_draws) b.step_env_draws += k * 4;
+    if (b.reset_env_draws) b.reset_env_draws += k * 4;
+    return b;
+}
+
+static cudaError_t launch_step_range(uavsim_handle* h, int e0, int n, const int32_t* actions, cudaStream_t st) {
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    const Buffers b = range_buffers(h, e0, n);
+    if (h->cfg.precision == UAVSIM_F64) {
+        Params<double> p = h->p64;
+        p.env_id_offset += e0;
+        return launch_step_f64(p, b, actions + e0, replay, st);
+    }
+    Params<float> p = h->p32;
+    p.env_id_offset += e0;
+    return launch_step_f32(p, b, actions + e0, replay, st);
+}
+
 int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
     if (int rc = check_ready(h, false)) return rc;
     if (!actions) return fail(UAVSIM_ERR_INVALID_ARG, "actions is NULL");
@@ -687,22 +744,63 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
                      uint8_t* done_host, void* stream) {
     if (!h || !actions_host || !reward_host || !done_host)
         return fail(UAVSIM_ERR_INVALID_ARG, "handle/actions/reward/done is NULL");
+    if (int rc = check_ready(h, false)) return rc;
+    if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t E = (size_t)h->cfg.num_envs;
-    CUDA_TRY(cudaMemcpyAsync(h->actions_dev, actions_host, E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (int rc = uavsim_step(h, h->actions_dev, stream)) return rc;
-    if (obs_host) {  // the stacked window [E][k*obs_dim] (a strided slice of the mirrored ring when k > 1)
-        const size_t k = (size_t)h->cfg.frame_stack, od = (size_t)h->dims.obs_dim;
-        if (ring_frames(h->cfg) == 1)
-            CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs, E * od * sizeof(float), cudaMemcpyDeviceToHost, st));
-        else
-            CUDA_TRY(cudaMemcpy2DAsync(obs_host, k * od * sizeof(float), h->buf.obs + (size_t)(h->frame_slot + 1) * od,
-                                       (size_t)h->dims.obs_row_floats * sizeof(float), k * od * sizeof(float), E,
-                                       cudaMemcpyDeviceToHost, st));
+    const int E = h->cfg.num_envs;
+    const size_t rb = (size_t)h->dims.real_bytes, od = (size_t)h->dims.obs_dim, k = (size_t)h->cfg.frame_stack;
+    // Ranges of a multiple of 64 environments (tile- and pair-aligned), at least 16 Ki each: below that the copies are
+    // latency-bound and one launch is as good.
+    int chunks = h->host_chunks;
+    while (chunks > 1 && E / chunks < 16384) chunks >>= 1;
+    const int per = ((E + chunks - 1) / chunks + 63) / 64 * 64;
+    if (chunks > 1 && !h->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& ev : h->ev_range) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaMemcpyAsync(reward_host, h->buf.reward, E * h->dims.real_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(done_host, h->buf.done, E, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->actions_dev, actions_host, (size_t)E * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    h->buf.step_serial += 1;
+    h->frame_slot = (h->frame_slot + 1) % ring_frames(h->cfg);
+    h->buf.frame_slot = h->frame_slot;
+    int c = 0;
+    for (int e0 = 0; e0 < E; e0 += per, ++c) {
+        const int n = E - e0 < per ? E - e0 : per;
+        cudaError_t le = launch_step_range(h, e0, n, h->actions_dev, st);
+        if (le != cudaSuccess) return cuda_fail(le, "step_kernel launch");
+        h->launches += 1;
+        cudaStream_t cs = st;
+        if (chunks > 1) {  // the copy-out of this range overlaps the step of the next one
+            cs = h->copy_stream;
+            CUDA_TRY(cudaEventRecord(h->ev_range[c], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs, h->ev_range[c], 0));
+        }
+        if (obs_host) {  // the stacked window [n][k * obs_dim] (a strided slice of the mirrored ring when K > 1)
+            const float* src = h->buf.obs + (size_t)e0 * (size_t)h->dims.obs_row_floats;
+            float* dst = obs_host + (size_t)e0 * k * od;
+            if (ring_frames(h->cfg) == 1)
+                CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * od * sizeof(float), cudaMemcpyDeviceToHost, cs));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(dst, k * od * sizeof(float), src + (size_t)(h->frame_slot + 1) * od,
+                                           (size_t)h->dims.obs_row_floats * sizeof(float), k * od * sizeof(float), (size_t)n,
+                                           cudaMemcpyDeviceToHost, cs));
+        }
+        CUDA_TRY(cudaMemcpyAsync((char*)reward_host + (size_t)e0 * rb, (const char*)h->buf.reward + (size_t)e0 * rb, (size_t)n * rb,
+                                 cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->buf.done + e0, (size_t)n, cudaMemcpyDeviceToHost, cs));
+    }
+    if (chunks > 1) {  // the caller's stream sees the copies as done, then the host waits for both
+        CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copied, 0));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
+    return UAVSIM_OK;
+}
+
+int uavsim_set_host_chunks(uavsim_handle* h, int32_t chunks) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    if (chunks != 1 && chunks != 2 && chunks != 4 && chunks != 8) return fail(UAVSIM_ERR_INVALID_ARG, "chunks must be 1, 2, 4 or 8");
+    h->host_chunks = chunks;
     return UAVSIM_OK;
 }
 

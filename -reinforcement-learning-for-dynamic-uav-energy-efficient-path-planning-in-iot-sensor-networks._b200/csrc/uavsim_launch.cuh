@@ -1,5 +1,6 @@
 // Launch entry points shared between the two kernel translation units and the C-ABI layer.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -82,6 +83,16 @@ inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool min4, cons
     *grid = dim3((unsigned)(need < blocks ? need : blocks));
 }
 
+// The packed kernel (uavsim_packed.cuh): float32, Philox, 3 features per sensor, one frame per environment, no wrapper,
+// even P.  L lanes per environment: 2 for P <= 32, 4 for P <= 64 (UAVSIM_PACK_L overrides, for sweeps).
+inline bool packed_eligible(const Params<float>& p, const Buffers& b, bool replay) {
+    static const bool off = getenv("UAVSIM_NO_PACKED") != nullptr;
+    return !off && !replay && p.fps == 3 && !p.relational && p.frame_k == 1 && !(p.gps_sigma > 0.f) && !(p.wind_drift > 0.0) &&
+           (p.P % 2) == 0 && p.P >= 2;
+}
+// defined in uavsim_f32.cu (the packed kernels exist in the throughput translation unit only)
+cudaError_t launch_packed(const Params<float>& p, const Buffers& b, const int32_t* actions, cudaStream_t st);
+
 template <typename Real>
 inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const int32_t* actions, bool replay,
                                  cudaStream_t st) {
@@ -96,6 +107,7 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
 #endif
         ;
     if constexpr (!std::is_same<Real, double>::value) {
+        if (packed_eligible(p, b, replay)) return launch_packed(p, b, actions, st);
         if (lean_base) {
             const bool stack = p.frame_k > 1;
             dim3 grid;

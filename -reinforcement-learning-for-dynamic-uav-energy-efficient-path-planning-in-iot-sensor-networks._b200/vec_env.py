@@ -53,6 +53,30 @@ _INFO_KEYS = ("uav_position", "battery", "battery_percent", "sensors_collected",
               "edge_steps", "last_step_bytes_collected", "sensor_collection_ratios")
 
 
+def numa_local_cpus(dev_index: int):
+    """(CPUs of the NUMA node the GPU hangs off that this process may run on, node id) from sysfs; (None, node) when
+    the topology cannot be read or the cpuset excludes that node."""
+    import os
+    import subprocess
+    from pathlib import Path
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(dev_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if len(bus.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(Path("/sys/bus/pci/devices/%s/numa_node" % bus).read_text())
+        if node < 0:
+            return None, node
+        cpus = set()
+        for part in Path("/sys/devices/system/node/node%d/cpulist" % node).read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (cpus or None), node
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -221,6 +245,7 @@ class UAVVecEnv(_VecEnvBase):
         self._np_infos = None
         self._np_dirty = []
         self._info_buf = None     # device rows of the on-demand _get_info kernel
+        self.host_numa = None
         self._next_seed = None
         if HAVE_SB3:              # VecEnv.__init__ (sets num_envs / spaces, reset_infos, _seeds, _options, render_mode)
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
@@ -339,12 +364,34 @@ class UAVVecEnv(_VecEnvBase):
         return self.obs, self.reward, self.done
 
     def make_host_buffers(self):
-        """Pinned host buffers for `step_host` (actions in; obs, reward, done out)."""
+        """Pinned host buffers for `step_host` (actions in; obs, reward, done out), allocated NUMA-local to the GPU:
+        the pages of a pinned allocation land on the node of the allocating thread, so the thread is moved onto the
+        CPUs of the GPU's node for the allocation (when the cpuset allows it) -- with eight ranks on a two-socket host
+        the copies of half the GPUs otherwise cross the socket interconnect.  `self.host_numa` records what was done."""
+        import os
         E = self.num_envs
-        return dict(actions=torch.zeros((E,), dtype=torch.int32).pin_memory(),
-                    obs=torch.empty((E, self.stacked_dim), dtype=torch.float32).pin_memory(),
-                    reward=torch.empty((E,), dtype=self.real_dtype).pin_memory(),
-                    done=torch.empty((E,), dtype=torch.uint8).pin_memory())
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cpus, node = numa_local_cpus(idx)
+        before = os.sched_getaffinity(0)
+        moved = False
+        if cpus and cpus != before:
+            try:
+                os.sched_setaffinity(0, cpus)
+                moved = True
+            except OSError:
+                moved = False
+        try:
+            bufs = dict(actions=torch.zeros((E,), dtype=torch.int32).pin_memory(),
+                        obs=torch.empty((E, self.stacked_dim), dtype=torch.float32).pin_memory(),
+                        reward=torch.empty((E,), dtype=self.real_dtype).pin_memory(),
+                        done=torch.empty((E,), dtype=torch.uint8).pin_memory())
+            bufs["obs"].zero_()          # first touch on the local node
+        finally:
+            if moved:
+                os.sched_setaffinity(0, before)
+        self.host_numa = {"gpu_numa_node": node, "cpus_allowed": len(before),
+                          "allocated_on_gpu_node": bool(moved or (cpus is not None and cpus == before))}
+        return bufs
 
     def step_host(self, host: dict, copy_obs=True):
         """The end-to-end call with HOST buffers (uavsim_step_host): actions host->device, one step,
@@ -641,6 +688,14 @@ class UAVVecEnv(_VecEnvBase):
         grids = self._apply_stage(self.cfg, stage)
         flat = (C.c_int32 * (2 * len(grids)))(*[v for g in grids for v in g])
         N.check(self.lib.uavsim_set_stage_grids(self._h, len(grids), flat))
+
+    def set_stage_grids(self, grids) -> None:
+        """Install an explicit grid list for DomainRandEnv resets (uavsim_set_stage_grids): the reference samples
+        from CURRICULUM_STAGES (100..500, dqn.py:63-69); BASELINE configs[2] words the sweep as 300..1000."""
+        grids = [(int(w), int(h)) for w, h in grids]
+        flat = (C.c_int32 * (2 * len(grids)))(*[v for g in grids for v in g])
+        N.check(self.lib.uavsim_set_stage_grids(self._h, len(grids), flat))
+        self._stage = -1
 
     def seed(self, seed: Optional[int] = None) -> Sequence[Optional[int]]:
         """VecEnv.seed: remembered and applied by the next `reset()` (one Philox key for the batch; env i's streams

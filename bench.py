@@ -41,6 +41,7 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = dict(name="configs[4]: scalability sweep 1000x1000, N=50, 1M envs per GPU, random actions, Philox",
                 grid=(1000, 1000), num_sensors=50, envs_per_gpu=1 << 20)
 METRIC = "env-steps/sec"
+KERNEL_NAME = "uavsim::packed_step_kernel<L=%d, MODE=plain, DIAG=false>"
 
 
 def bytes_per_env_step(n_sensors: int, precision: str = "f32", obs_floats: int | None = None) -> int:
@@ -58,6 +59,12 @@ def bytes_per_env_step(n_sensors: int, precision: str = "f32", obs_floats: int |
     per_env += 4 * (obs_floats if obs_floats is not None else 3 + 3 * n_sensors)   # observation row
     per_env += rb + 1                # reward, done
     return per_sensor * n_sensors + per_env
+
+
+def bytes_per_env_step_survey(n_sensors: int) -> int:
+    """SURVEY.md section 8(d)'s own estimate for the float32 layout: 42 N + 746 (a 64-byte env record instead of
+    the 128-byte one that was built)."""
+    return 42 * n_sensors + 746
 
 
 # ----------------------------------------------------------------------------------------------
@@ -147,7 +154,10 @@ def run_reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "grid": list(grid), "num_sensors": n,
                        "envs_per_step": cores * envs_per_core,
-                       "note": "bounded sample of the workload; the reference is pure Python and scales by processes"},
+                       "note": "bounded sample of the workload; the reference is pure Python and scales by processes. "
+                               "This arm is the pinned numpy PORT of the reference step (oracle/uavsim_oracle.py): it runs "
+                               "~4x faster per core than the reference's own classes (BASELINE.md section 2: ~450 steps/s/core "
+                               "at N=50), so ratios against it are conservative"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -228,18 +238,9 @@ def run_gpu_arm(args):
     E = args.envs or WORKLOAD["envs_per_gpu"]
     n = args.sensors or WORKLOAD["num_sensors"]
     grid = WORKLOAD["grid"]
-    env = pkg.UAVVecEnv(E, grid_size=grid, num_sensors=n, precision="f32", rng="philox", seed=20261018,
-                        env_id_offset=rank * E, auto_reset=True, device=str(dev), action_mask=False)
-    env.reset_tensors()
     n_act = 8
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    # Steady state instead of 1M synchronised fresh episodes: start every UAV at a random state of charge, so that
-    # truncations, terminal penalties and in-kernel restarts happen inside the timed region at the rate of a long run
-    # (a full battery lasts ~1790 random steps -- longer than the default timed region).
-    env.set_battery(5.48 + (274.0 - 5.48) * torch.rand(E, device=dev, generator=g, dtype=torch.float64))
-    actions = [torch.randint(0, 5, (E,), dtype=torch.int32, device=dev, generator=g) for _ in range(n_act)]
     stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -247,33 +248,80 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ----
-    for t in range(args.warmup):
-        env.step_tensors(actions[t % n_act])
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = env.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for t in range(args.steps):
-        env.step_tensors(actions[t % n_act])
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = env.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_env(envs, sensors, **kw):
+        env = pkg.UAVVecEnv(envs, grid_size=kw.pop("grid_size", grid), num_sensors=sensors, precision="f32", rng="philox",
+                            seed=20261018, env_id_offset=rank * envs, auto_reset=True, device=str(dev), action_mask=False,
+                            terminal_info=False, **kw)
+        env.reset_tensors()
+        return env
+
+    def make_actions(envs, p_collect=None, seed=1234):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + rank)
+        acts = []
+        for _ in range(n_act):
+            a = torch.randint(0, 5 if p_collect is None else 4, (envs,), dtype=torch.int32, device=dev, generator=g)
+            if p_collect is not None:   # a driver's action mix: the reference's greedy agents collect on ~98 % of steps
+                a = torch.where(torch.rand(envs, device=dev, generator=g) < p_collect, torch.full_like(a, 4), a)
+            acts.append(a)
+        return acts, g
+
+    def desync(env, g):
+        # Steady state instead of synchronised fresh episodes: every UAV starts at a random state of charge, so that
+        # truncations, terminal penalties and in-kernel restarts happen inside the timed region at the rate of a long
+        # run (a full battery lasts ~1790 random steps -- longer than the default timed region).
+        env.set_battery(5.48 + (274.0 - 5.48) * torch.rand(env.num_envs, device=dev, generator=g, dtype=torch.float64))
+
+    def time_steps(env, acts, steps, warm, sync_ranks=False, sample_clocks=False):
+        """CUDA-event time of `steps` launches after `warm` untimed ones; max over ranks when sync_ranks."""
+        for t in range(warm):
+            env.step_tensors(acts[t % n_act])
+        (barrier if sync_ranks else (lambda: torch.cuda.synchronize(dev)))()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = env.launch_count
+        (barrier if sync_ranks else (lambda: torch.cuda.synchronize(dev)))()
+        ev0.record(stream)
+        for t in range(steps):
+            env.step_tensors(acts[t % n_act])
+        ev1.record(stream)
+        (barrier if sync_ranks else (lambda: torch.cuda.synchronize(dev)))()
+        ms = ev0.elapsed_time(ev1)
+        launches = env.launch_count - l0
+        clocks = sampler.stop() if sampler else None
+        return (allmax(ms) if sync_ranks else ms), launches, clocks
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- headline: device-resident throughput, weak scaling (1 M envs per GPU) ----
+    env = make_env(E, n)
+    actions, g = make_actions(E)
+    desync(env, g)
+    ms_max, launches, clocks = time_steps(env, actions, args.steps, args.warmup, sync_ranks=True, sample_clocks=(rank == 0))
     env.poll_errors()
     # the one collective of the path: episode statistics (off the step's critical path)
     sums = env.stat_sums.clone()
     if world > 1:
         dist.all_reduce(sums)
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
+
+    # ---- sustained: the same loop for >= 2 s (power-capped rate), its own clock record ----
+    sustained = None
+    if args.sustained_s > 0:
+        k_s = max(args.steps, int(args.sustained_s * 1e3 / max(ms_max / args.steps, 1e-3)))
+        ms_s, _, clk_s = time_steps(env, actions, k_s, 0, sync_ranks=True, sample_clocks=(rank == 0))
+        sustained = {"steps": k_s, "seconds": ms_s / 1e3, "ms_per_step": ms_s / k_s, "value": E * world * k_s / (ms_s * 1e-3),
+                     "roofline_frac": bytes_per_env_step(n) * E * k_s / (ms_s * 1e-3) / 1e9 / peak, "clocks": clk_s}
 
     # ---- end to end through the host-buffer call ----
     host = env.make_host_buffers()
@@ -290,31 +338,61 @@ def run_gpu_arm(args):
         env.step_host(host)
     ev1.record(stream)
     barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    tms = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tms.item())
+    e2e_ms = allmax(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
     obs_dim = env.dims.obs_dim
     h2d = E * 4
     d2h = E * (obs_dim * 4 + 4 + 1)
+    # the ceiling of that call: the same bytes as plain pinned copies (no kernel), all ranks at once
+    for _ in range(2):
+        host["obs"].copy_(env.obs, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for t in range(e2e_steps):
+        env._actions_dev.copy_(host["actions"], non_blocking=True)
+        host["obs"].copy_(env.obs, non_blocking=True)
+        host["reward"].copy_(env.reward, non_blocking=True)
+        host["done"].copy_(env.done, non_blocking=True)
+        stream.synchronize()
+    ev1.record(stream)
+    barrier()
+    copy_ms = allmax(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    e2e = {"value": E * world * e2e_steps / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "api": "UAVVecEnv.step_host -> uavsim_step_host (pinned host buffers, 4 env ranges: copy-out of range k overlaps the step of k+1)",
+           "pcie_roofline": {"what": "the same H2D + D2H bytes per step as plain pinned cudaMemcpyAsync copies, no kernel, all %d ranks at once" % world,
+                             "ms_per_step": copy_ms / e2e_steps, "value": E * world * e2e_steps / (copy_ms * 1e-3),
+                             "gb_per_s_per_rank": (h2d + d2h) * e2e_steps / (copy_ms * 1e-3) / 1e9,
+                             "frac": copy_ms / e2e_ms},
+           "host_numa": env.host_numa}
+    env.close()
+
+    # ---- strong scaling: BASELINE configs[4] as worded -- 1,048,576 envs split over the GPUs ----
+    strong = None
+    if world > 1 and not args.envs:
+        es = WORKLOAD["envs_per_gpu"] // world
+        env_s = make_env(es, n)
+        acts_s, g_s = make_actions(es)
+        desync(env_s, g_s)
+        k_s = min(args.steps, 300)
+        ms_s, _, _ = time_steps(env_s, acts_s, k_s, 5, sync_ranks=True)
+        strong = {"global_envs": es * world, "envs_per_gpu": es, "steps": k_s, "ms_per_step": ms_s / k_s,
+                  "value": es * world * k_s / (ms_s * 1e-3),
+                  "roofline_frac_per_gpu": bytes_per_env_step(n) * es * k_s / (ms_s * 1e-3) / 1e9 / peak}
+        env_s.close()
 
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bpe = bytes_per_env_step(n, "f32")
-        launch_ms = ms / max(launches, 1)
+        launch_ms = ms_max / max(launches, 1)
         achieved = bpe * E / (launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = ROOT / "profiles" / "dram_traffic.json"
         if tpath.exists():
             try:
                 tj = json.loads(tpath.read_text())
                 if tj.get("envs") == E and tj.get("num_sensors") == n:
                     traffic = tj.get("dram_bytes_per_launch")
+                    traffic_src = "profiles/dram_traffic.json (one `ncu --set full` capture of this kernel, committed; not measured in this run): " + str(tj.get("source"))
             except Exception:  # noqa: BLE001
                 pass
         cpu = None
@@ -322,30 +400,50 @@ def run_gpu_arm(args):
         if not args.no_cpu:
             cpu = cpu_python_port(grid, n, envs_per_core=4, warm=5, steps=args.cpu_steps)
             cpu_c = cpu_c_port(grid, n, n_envs=8192, steps=20)
-        secondary = None
+        secondaries = {}
         if not args.sensors and not args.no_secondary:
-            # the metric is quoted for N = 20-50: the same workload at N = 20 (pair kernel: two environments per warp pass)
-            env.close()
-            n2 = 20
-            env2 = pkg.UAVVecEnv(E, grid_size=grid, num_sensors=n2, precision="f32", rng="philox", seed=20261018,
-                                 env_id_offset=rank * E, auto_reset=True, device=str(dev), action_mask=False)
-            env2.reset_tensors()
-            for t in range(5):
-                env2.step_tensors(actions[t % n_act])
-            torch.cuda.synchronize(dev)
             k2 = min(args.steps, 300)
-            ev0.record(stream)
-            for t in range(k2):
-                env2.step_tensors(actions[t % n_act])
-            ev1.record(stream)
-            torch.cuda.synchronize(dev)
-            ms2 = ev0.elapsed_time(ev1) / k2
-            bpe2 = bytes_per_env_step(n2, "f32")
-            secondary = {"num_sensors": n2, "envs_per_gpu": E, "steps": k2, "ms_per_step": ms2,
-                         "value_per_gpu": E / (ms2 * 1e-3), "bytes_per_env_step": bpe2,
-                         "roofline_frac": bpe2 * E / (ms2 * 1e-3) / 1e9 / peak,
-                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=1, FPS=3, STACK=false, LEAN=plain, PAIR=true>"}
-            env2.close()
+
+            def second(name, envs, sensors, acts_kw=None, bpe2=None, note=None, **kw):
+                e2 = make_env(envs, sensors, **kw)
+                acts2, g2 = make_actions(envs, **(acts_kw or {}))
+                desync(e2, g2)
+                ms2, _, _ = time_steps(e2, acts2, k2, 5)
+                ms2 /= k2
+                bpe2 = bpe2 if bpe2 is not None else bytes_per_env_step(int(sensors) if not hasattr(sensors, "__len__") else 0)
+                secondaries[name] = {"envs_per_gpu": envs, "steps": k2, "ms_per_step": ms2, "value_per_gpu": envs / (ms2 * 1e-3),
+                                     "bytes_per_env_step": bpe2, "roofline_frac": bpe2 * envs / (ms2 * 1e-3) / 1e9 / peak,
+                                     "episodes_finished": float(e2.stat_sums[-1].item())}
+                if note:
+                    secondaries[name]["note"] = note
+                e2.close()
+
+            # the metric is quoted for N = 20-50: the same workload at N = 20
+            second("n20", E, 20)
+            secondaries["n20"]["num_sensors"] = 20
+            # the action mix of the reference's own drivers (greedy_agents.py:73-100 collect on ~98 % of steps): a COLLECT
+            # step costs 4N + W Gaussians and the capture resolution instead of 2N
+            second("n50_collect98", E, n, acts_kw=dict(p_collect=0.98), note="p(COLLECT) = 0.98 instead of 0.2")
+            # BASELINE configs[2]: 65,536 DomainRandEnv environments, N = 10..50 padded to 50 observation slots, grids
+            # 300..1000, in-kernel restarts with far-start search
+            import numpy as np
+            ns = np.random.default_rng(0).integers(10, 51, size=65536).astype(np.int32)
+            e3 = pkg.UAVVecEnv(65536, num_sensors=ns, max_sensors=50, domain_randomisation=True, curriculum_stage=4,
+                               seed=9, action_mask=False, terminal_info=False, device=str(dev))
+            e3.set_stage_grids([(w, w) for w in range(300, 1001, 100)])
+            e3.reset_tensors()
+            acts3, g3 = make_actions(65536)
+            desync(e3, g3)
+            ms3, _, _ = time_steps(e3, acts3, k2 * 4, 20)
+            ms3 /= k2 * 4
+            b3 = float(np.mean([bytes_per_env_step(int(v), obs_floats=3 + 3 * int(v)) for v in ns]))
+            secondaries["config3_domain_rand_65536"] = {
+                "envs_per_gpu": 65536, "steps": k2 * 4, "ms_per_step": ms3, "value_per_gpu": 65536 / (ms3 * 1e-3),
+                "bytes_per_env_step": b3, "roofline_frac": b3 * 65536 / (ms3 * 1e-3) / 1e9 / peak,
+                "episodes_finished": float(e3.stat_sums[-1].item()),
+                "note": "BASELINE configs[2]; 0.2 GB of state per launch: the working set is L2-sized, the launch is short "
+                        "(latency / tail bound), so the HBM fraction understates it"}
+            e3.close()
         total_steps = E * world * args.steps
         line = {
             "metric": METRIC, "value": total_steps / (ms_max * 1e-3), "unit": METRIC, "n_gpus": world,
@@ -353,26 +451,30 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "grid": list(grid), "num_sensors": n, "envs_per_gpu": E,
                        "global_envs": E * world, "precision": "f32 state / f64 battery+returns", "rng": "philox4x32-10",
-                       "actions": "uniform random, %d pre-generated device tensors cycled" % n_act,
+                       "actions": "uniform random (p(COLLECT) = 0.2), %d pre-generated device tensors cycled" % n_act,
                        "auto_reset": True, "initial_state": "random state of charge per env (episodes end inside the timed region)", "parallelism": "env-sharded x%d, no data-path collective" % world,
                        "l2": "state per launch %.2f GB >> 126 MB L2 (inputs larger than L2)" % (bpe * E / 1e9)},
             "clocks": clocks,
-            "e2e": {"value": E * world * e2e_steps / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "UAVVecEnv.step_host -> uavsim_step_host (pinned host buffers)"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bpe,
-                         "kernel": "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=plain>" % (2 if n > 32 else 1),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "bytes_per_env_step": bpe, "bytes_model": "layout as built: 56 N + 277 (DESIGN.md section 3)",
+                         "frac_survey_model": bytes_per_env_step_survey(n) * E / (launch_ms * 1e-3) / 1e9 / peak,
+                         "bytes_per_env_step_survey_model": bytes_per_env_step_survey(n),
+                         "kernel": KERNEL_NAME % (4 if n > 32 else 2),
                          "launch_ms": launch_ms},
+            "sustained": sustained,
+            "strong_scaling": strong,
             "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cpu_baseline_native": cpu_c,
-            "secondary_n20_rank0": secondary,
+            "secondary_n20_rank0": secondaries.get("n20"),
+            "secondary_collect98_rank0": secondaries.get("n50_collect98"),
+            "secondary_config3_rank0": secondaries.get("config3_domain_rand_65536"),
             "episode_stats": {"episodes_finished": float(sums[-1].item()),
                               "mean_return": float(sums[0].item() / max(sums[-1].item(), 1.0))},
         }
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -388,7 +490,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the N=20 secondary measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements (N=20, collect-heavy, configs[2])")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="seconds of the extra sustained (power-capped) loop; 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

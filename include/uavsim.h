@@ -341,11 +341,15 @@ int uavsim_reset(uavsim_handle* h, const uint8_t* env_mask_dev, void* stream);
 /* One environment step for every env: uav_env.py:429-488 (+ dqn.py:415-444 in DOMAIN_RAND mode).
  * actions_dev: [E] int32 in [0,4].  Writes obs, reward, done (+ optional outputs). */
 int uavsim_step(uavsim_handle* h, const int32_t* actions_dev, void* stream);
-/* Same step with HOST buffers: copies actions host->device, steps, copies obs/reward/done back,
- * all on `stream`, then synchronises the stream.  Buffers should be pinned for full PCIe rate.
- * obs_host may be NULL to skip that copy. */
+/* Same step with HOST buffers: copies actions host->device, steps, copies obs/reward/done back, then synchronises
+ * `stream`.  Pipelined: the batch is stepped as up to uavsim_set_host_chunks (default 4) env ranges, and the copy-out
+ * of range k runs on an internal stream while range k+1 is stepped (environments are independent and their draws are
+ * keyed by the global env id, so the result is bit-identical to one launch); batches under 32 Ki envs take one launch.
+ * Buffers should be pinned (and NUMA-local to the GPU) for full PCIe rate.  obs_host may be NULL to skip that copy. */
 int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_host, void* reward_host,
                      uint8_t* done_host, void* stream);
+/* Number of env ranges uavsim_step_host pipelines over: 1 (no overlap), 2, 4 or 8. */
+int uavsim_set_host_chunks(uavsim_handle* h, int32_t chunks);
 
 /* ---- on-device heuristic driver ------------------------------- */
 /* NearestSensorGreedy.select_action for every env (greedy_agents.py:73-100, :41-68): COLLECT if a sensor with

@@ -350,6 +350,15 @@ __device__ __forceinline__ void adr_update(const Params<Real>& p, Real rssi, Rea
     ema = (ema != ema) ? rssi : blended;  // NaN = None: the first sample initialises the average
     // the reference takes the FIRST match of the descending ladder -60 / -70 / -78 / -85 (iot_sensors.py:252-255),
     // which is the LAST assignment of the ascending one
+#ifdef UAVSIM_ADR_IMM  // A/B switch: thresholds as immediates (valid for rssi_threshold = -85 only)
+    if constexpr (!std::is_same<Real, double>::value) {
+        sf = ema > 0.0f ? 12 : sf;
+        sf = ema > 7.0f ? 11 : sf;
+        sf = ema > 15.0f ? 9 : sf;
+        sf = ema > 25.0f ? 7 : sf;
+        return;
+    }
+#endif
     sf = ema > p.adr_t85 ? 12 : sf;
     sf = ema > p.adr_t78 ? 11 : sf;
     sf = ema > p.adr_t70 ? 9 : sf;

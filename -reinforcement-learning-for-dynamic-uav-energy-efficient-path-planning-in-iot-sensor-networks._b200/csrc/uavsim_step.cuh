@@ -249,7 +249,11 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
     // from its float32 inputs: the terms reach 7e4 (100 * bytes * urgency) and can cancel down to O(1), where a
     // float32 running sum would leave ~1e-4 of absolute rounding; the cost is a dozen DADD / DFMA per COLLECT step,
     // identical in every lane.
+#ifdef UAVSIM_F32_REWARD  // A/B switch (tools/build_variants.py)
+    using Acc = Real;
+#else
     using Acc = double;
+#endif
     Acc reward = (Acc)p.p_step + (Acc)p.p_hover;
     if (total_bytes > Real(0)) {
         reward += (Acc)p.r_per_byte * (Acc)total_bytes * (Acc)mean_urg;
@@ -278,7 +282,25 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
                     dev[k] = s[k].active ? d * d : Real(0);
                 }
                 reward += p.p_starvation * (sensor_sum<Real, SPL>(dev, N, lane, ws.red, kSumNumpy) / (Real)N);
-            } else {  // the same two passes on shuffle trees (the one-pass E[x^2] - E[x]^2 cancels: x is in [0, 1])
+            } else {
+#ifdef UAVSIM_ONEPASS_VAR  // A/B switch: round-1 form, var = E[x^2] - E[x]^2 on one fused shuffle tree
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const float v = s[k].active ? s[k].buf : 0.f;
+                    s1 += v;
+                    s2 = fmaf(v, v, s2);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    s1 += __shfl_xor_sync(kFull, s1, o);
+                    s2 += __shfl_xor_sync(kFull, s2, o);
+                }
+                const float inv = fast_rcp(mx), invn = fast_rcp((float)N);
+                const float mean = s1 * inv * invn;
+                reward += (Acc)p.p_starvation * (Acc)fmaxf(fmaf(s2 * inv * inv, invn, -mean * mean), 0.f);
+#else
+                // the same two passes on shuffle trees (the one-pass E[x^2] - E[x]^2 cancels: x is in [0, 1])
                 // MUFU.RCP + one Newton step: the reciprocals scale every x (and the variance twice)
                 float inv = fast_rcp(mx), invn = fast_rcp((float)N);
                 inv = fmaf(inv, fmaf(-mx, inv, 1.0f), inv);
@@ -297,6 +319,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
                     s2 = s[k].active ? fmaf(d, d, s2) : s2;
                 }
                 reward += (Acc)p.p_starvation * (Acc)(warp_sum(s2) * invn);
+#endif
             }
         }
     }
@@ -420,9 +443,11 @@ __device__ __noinline__ void finish_and_restart(const Params<Real>& p, const Buf
     Sensor<Real> s[SPL];
     load_sensors<Real, SPL>(b, p, e, N, lane, s);
     write_episode_stats<Real, SPL>(p, b, e, lane, ws.rec, s);
+#ifndef UAVSIM_NO_TINFO  // A/B switch
     if (b.terminal_info || b.terminal_ratios)
         write_info<Real, SPL>(p, lane, ws.rec, s, ws.red, b.terminal_info ? b.terminal_info + (size_t)e * UAVSIM_INFO_COUNT : nullptr,
                               b.terminal_ratios ? b.terminal_ratios + (size_t)e * p.P : nullptr);
+#endif
     reset_env<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws, s, (Real*)nullptr);
     store_sensors<Real, SPL>(b, p, e, lane, s, true);
 }

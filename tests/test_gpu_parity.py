@@ -170,7 +170,7 @@ def test_float32_throughput_build_against_the_oracle(pkg, name):
            {k: "%.1e" % v for k, v in res["per_key"].items()}, res["reward_abs_over_scale"],
            res.get("rewards_uncancelled", 0), res.get("rewards_compared", 0), res.get("reward_rel_uncancelled", 0.0)))
     assert sensor_steps >= 10 ** 6
-    assert res["unmargined_flips"] == 0, res                 # every discrete difference is a justified flip
+    assert res["unmargined_flips"] == 0, (res.get("flip_names", [])[:12], res["first_bad"])                # every discrete difference is a justified flip
     assert res["discrete_mismatches"] == 0, res
     assert res["flips"] <= max(4, 4e-6 * sensor_steps), res  # and they are rare: ~0.5 per million sensor-steps measured
     pk = res["per_key"]

@@ -685,6 +685,11 @@ static Buffers range_buffers(const uavsim_handle* h, int e0, int n) {
     return b;
 }
 
+static int step_launches(const uavsim_handle* h) {
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
+    return h->cfg.precision == UAVSIM_F64 ? step_launch_count(h->p64, h->buf, replay) : step_launch_count(h->p32, h->buf, replay);
+}
+
 static cudaError_t launch_step_range(uavsim_handle* h, int e0, int n, const int32_t* actions, cudaStream_t st) {
     const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY;
     const Buffers b = range_buffers(h, e0, n);
@@ -709,7 +714,7 @@ int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
     cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_step_f64(h->p64, h->buf, actions, replay, (cudaStream_t)stream)
                                                    : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "step_kernel launch");
-    h->launches += 1;
+    h->launches += step_launches(h);
     return UAVSIM_OK;
 }
 
@@ -768,7 +773,7 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
         const int n = E - e0 < per ? E - e0 : per;
         cudaError_t le = launch_step_range(h, e0, n, h->actions_dev, st);
         if (le != cudaSuccess) return cuda_fail(le, "step_kernel launch");
-        h->launches += 1;
+        h->launches += step_launches(h);
         cudaStream_t cs = st;
         if (chunks > 1) {  // the copy-out of this range overlaps the step of the next one
             cs = h->copy_stream;

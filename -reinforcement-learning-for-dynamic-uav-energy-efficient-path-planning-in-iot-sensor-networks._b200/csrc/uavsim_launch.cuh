@@ -83,31 +83,30 @@ inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool min4, cons
     *grid = dim3((unsigned)(need < blocks ? need : blocks));
 }
 
-// The packed kernel (uavsim_packed.cuh): float32, Philox, 3 features per sensor, one frame per environment, no wrapper,
-// even P.  L lanes per environment: 2 for P <= 32, 4 for P <= 64 (UAVSIM_PACK_L overrides, for sweeps).
-inline bool packed_eligible(const Params<float>& p, const Buffers& b, bool replay) {
-    static const bool off = getenv("UAVSIM_NO_PACKED") != nullptr;
-    return !off && !replay && p.fps == 3 && !p.relational && p.frame_k == 1 && !(p.gps_sigma > 0.f) && !(p.wind_drift > 0.0) &&
-           (p.P % 2) == 0 && p.P >= 2;
+// Throughput build, Philox, no diagnostics: the plain UAVEnvironment step, the DomainRandEnv training step and the
+// RelationalUAVEnv step run LEAN instantiations (the features they do not use are compiled out, finished episodes restart
+// in a second launch); everything else takes the generic kernel.
+template <typename Real>
+inline bool lean_eligible(const Params<Real>& p, const Buffers& b, bool replay) {
+#ifdef UAVSIM_NO_LEAN
+    return false;
+#else
+    return !std::is_same<Real, double>::value && !replay && !b.draw_export && !b.step_detail && !(p.gps_sigma > Real(0)) &&
+           !(p.wind_drift > 0.0) && ((p.fps == 3 && !p.relational) || (p.fps == 5 && p.relational && !p.domain_rand));
+#endif
 }
-// defined in uavsim_f32.cu (the packed kernels exist in the throughput translation unit only)
-cudaError_t launch_packed(const Params<float>& p, const Buffers& b, const int32_t* actions, cudaStream_t st);
+// Kernels one step launches: the LEAN kernels hand finished episodes to restart_kernel.
+template <typename Real>
+inline int step_launch_count(const Params<Real>& p, const Buffers& b, bool replay) {
+    return lean_eligible(p, b, replay) && p.auto_reset ? 2 : 1;
+}
 
 template <typename Real>
 inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const int32_t* actions, bool replay,
                                  cudaStream_t st) {
     const bool two = p.P > 32;
-    // Throughput build, Philox, no diagnostics: the plain UAVEnvironment step and the DomainRandEnv training step run
-    // LEAN instantiations (the features they do not use are compiled out); everything else takes the generic kernel.
-    const bool lean_base = !std::is_same<Real, double>::value && !replay && !b.draw_export && !b.step_detail &&
-                           !(p.gps_sigma > Real(0)) && !(p.wind_drift > 0.0) &&
-                           ((p.fps == 3 && !p.relational) || (p.fps == 5 && p.relational && !p.domain_rand))
-#ifdef UAVSIM_NO_LEAN
-                           && false
-#endif
-        ;
+    const bool lean_base = lean_eligible(p, b, replay);
     if constexpr (!std::is_same<Real, double>::value) {
-        if (packed_eligible(p, b, replay)) return launch_packed(p, b, actions, st);
         if (lean_base) {
             const bool stack = p.frame_k > 1;
             dim3 grid;
@@ -119,6 +118,10 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
         auto k = stack ? step_kernel<Real, false, S, F, true, MODE, PAIRED> : step_kernel<Real, false, S, F, false, MODE, PAIRED>; \
         launch_step_kernel(k, smem, warps, true, b, &grid, &bb);                                            \
         k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                                    \
+        if (p.auto_reset) { /* finished episodes restart in their own launch (uavsim_step.cuh, restart_kernel) */ \
+            auto rk = restart_kernel<Real, false, S, F>;                                                      \
+            rk<<<persistent_grid(rk, (b.E + 31) / 32), kThreads, 0, st>>>(p, bb);                             \
+        }                                                                                                     \
     } while (0)
             if (p.relational) {  // RelationalUAVEnv rows (5 features per sensor)
                 if (two)

@@ -799,6 +799,11 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 const int32_t* __restrict__ actions) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
+    // LEAN instantiations leave finished episodes to restart_kernel (launched right behind this one on the same
+    // stream): the out-of-line restart path -- episode statistics, terminal info, DomainRandEnv scenario draws with
+    // the far-start search, first observation -- costs the hot loop registers and instruction cache even though it
+    // almost never runs (the terminal-info call alone: 0.65 -> 0.74 ms per launch at N = 50, profiles/README.md).
+    constexpr bool kDeferredRestart = LEAN != kGeneric;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(!PAIR || ((LEAN == kLeanPlain || LEAN == kLeanDomainRand) && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
@@ -875,6 +880,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             ts.episode[lane] = R.w(kREpisode);
             if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
                 atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
+                if constexpr (kDeferredRestart) b.done[e] = 0;  // restart_kernel goes by the done flags of THIS step
             } else {
                 my_flags = kFlagValid;
                 float x = R.f(kRX), y = R.f(kRY);
@@ -1197,6 +1203,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         __syncwarp();
 
         // ---- SB3 VecEnv semantics: finished episodes restart inside the same call (rare) ----
+        if constexpr (kDeferredRestart) restart_mask = 0u;
         while (restart_mask) {
             const int k = __ffs(restart_mask) - 1;
             restart_mask &= restart_mask - 1;
@@ -1237,6 +1244,29 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
 #undef UAVSIM_E
 #undef UAVSIM_NEXT_BASE
 #undef UAVSIM_TAKE_TICKET
+}
+
+// Finished episodes of the step just launched (done flag set): terminal observation, episode statistics, terminal
+// info, new episode -- DummyVecEnv's reset-on-done, for the LEAN step kernels.  One warp per finished environment;
+// a warp scans 32 done flags at a time.
+template <typename Real, bool REPLAY, int SPL, int FPS>
+__global__ void __launch_bounds__(kThreads) restart_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b) {
+    __shared__ WarpSmem smem[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& ws = smem[warp];
+    const int nchunks = (b.E + 31) / 32;
+    for (int c = blockIdx.x * kWarpsPerBlock + warp; c < nchunks; c += gridDim.x * kWarpsPerBlock) {
+        const int e0 = c * 32 + lane;
+        unsigned m = __ballot_sync(kFull, e0 < b.E && b.done[e0] != 0);
+        while (m) {
+            const int e = c * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            load_record(ws, b.rec + e, lane);
+            finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
+            store_record(ws, b.rec + e, lane);
+            __syncwarp();
+        }
+    }
 }
 
 }  // namespace uavsim

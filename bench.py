@@ -41,7 +41,7 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = dict(name="configs[4]: scalability sweep 1000x1000, N=50, 1M envs per GPU, random actions, Philox",
                 grid=(1000, 1000), num_sensors=50, envs_per_gpu=1 << 20)
 METRIC = "env-steps/sec"
-KERNEL_NAME = "uavsim::packed_step_kernel<L=%d, MODE=plain, DIAG=false>"
+KERNEL_NAME = "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=plain%s> (+ restart_kernel for finished episodes, same stream)"
 
 
 def bytes_per_env_step(n_sensors: int, precision: str = "f32", obs_floats: int | None = None) -> int:
@@ -383,7 +383,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         bpe = bytes_per_env_step(n, "f32")
-        launch_ms = ms_max / max(launches, 1)
+        launch_ms = ms_max / args.steps      # per step: the step kernel + the restart kernel behind it (a few us)
         achieved = bpe * E / (launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tpath = ROOT / "profiles" / "dram_traffic.json"
@@ -462,7 +462,7 @@ def run_gpu_arm(args):
                          "bytes_per_env_step": bpe, "bytes_model": "layout as built: 56 N + 277 (DESIGN.md section 3)",
                          "frac_survey_model": bytes_per_env_step_survey(n) * E / (launch_ms * 1e-3) / 1e9 / peak,
                          "bytes_per_env_step_survey_model": bytes_per_env_step_survey(n),
-                         "kernel": KERNEL_NAME % (4 if n > 32 else 2),
+                         "kernel": KERNEL_NAME % ((2, "") if n > 32 else (1, ", PAIR=true")),
                          "launch_ms": launch_ms},
             "sustained": sustained,
             "strong_scaling": strong,

@@ -67,7 +67,7 @@ class Config(C.Structure):
         ("penalty_hover", _d), ("penalty_step", _d), ("penalty_data_loss", _d), ("penalty_starvation", _d),
         ("penalty_unvisited", _d), ("penalty_starved", _d), ("starvation_cr_threshold", _d),
         ("num_grids", _i32), ("grids", (_i32 * 2) * MAX_GRIDS),
-        ("min_start_dist", _d), ("max_start_tries", _i32), ("reserved1", _i32), ("prox_eta", _d), ("jain_bonus", _d),
+        ("min_start_dist", _d), ("max_start_tries", _i32), ("gps_in_observation", _i32), ("prox_eta", _d), ("jain_bonus", _d),
         ("rel_gamma", _d), ("rel_dwell_bonus", _d), ("rel_reward_scale", _d), ("rel_dwell_steps", _i32),
         ("rel_min_cluster", _i32),
         ("gps_sigma", _d), ("wind_drift", _d), ("latency_steps", _i32), ("reserved2", _i32),
@@ -134,7 +134,9 @@ SYMBOLS = (
     "uavsim_step_host", "uavsim_poll_error", "uavsim_stat_sums", "uavsim_launch_count", "uavsim_frame_slot",
     "uavsim_policy_nearest_greedy", "uavsim_policy_max_throughput_greedy",
     "uavsim_get_info", "uavsim_set_seed", "uavsim_set_frame_slot", "uavsim_set_host_chunks",
+    "uavsim_step_ex", "uavsim_set_env_params",
 )
+STEP_EXTRA = 1
 
 
 class UavsimError(RuntimeError):
@@ -187,6 +189,8 @@ def load() -> C.CDLL:
     lib.uavsim_set_seed.argtypes = [vp, C.c_uint64]
     lib.uavsim_set_frame_slot.argtypes = [vp, _i32]
     lib.uavsim_set_host_chunks.argtypes = [vp, _i32]
+    lib.uavsim_step_ex.argtypes = [vp, vp, vp, C.c_uint32, vp]
+    lib.uavsim_set_env_params.argtypes = [vp, vp, vp]
     if lib.uavsim_abi_version() != 2:
         raise ImportError("libuavsim.so ABI version mismatch")
     _lib = lib

@@ -86,6 +86,10 @@ int validate(const uavsim_config* c) {
     if (!(c->gps_sigma >= 0.0) || !(c->wind_drift >= 0.0)) return fail(UAVSIM_ERR_INVALID_ARG, "gps_sigma / wind_drift must be >= 0");
     if (c->wrapper != UAVSIM_WRAP_NONE && c->wrapper != UAVSIM_WRAP_RELATIONAL)
         return fail(UAVSIM_ERR_INVALID_ARG, "wrapper must be UAVSIM_WRAP_NONE or UAVSIM_WRAP_RELATIONAL");
+    if (c->gps_in_observation != 0 && c->gps_in_observation != 1)
+        return fail(UAVSIM_ERR_INVALID_ARG, "gps_in_observation must be 0 or 1");
+    if (c->gps_in_observation && (c->reset_mode != UAVSIM_RESET_FIXED || c->wrapper != UAVSIM_WRAP_NONE))
+        return fail(UAVSIM_ERR_INVALID_ARG, "gps_in_observation (PerturbedDQNEnv) sits on the plain UAVEnvironment");
     if (c->wrapper == UAVSIM_WRAP_RELATIONAL) {
         if (c->features_per_sensor != 5)
             return fail(UAVSIM_ERR_INVALID_ARG, "the relational wrapper needs features_per_sensor == 5 (env_wrapper.py:147)");
@@ -185,6 +189,7 @@ Params<Real> make_params(const uavsim_config& c) {
     p.rel_dwell_bonus = (Real)c.rel_dwell_bonus;
     p.rel_scale = (Real)c.rel_reward_scale;
     p.gps_sigma = (Real)c.gps_sigma;
+    p.gps_in_obs = c.gps_in_observation;
     p.wind_drift = c.wind_drift;
     p.max_battery = c.max_battery;
     p.batt_floor = 0.02 * c.max_battery;                       // uav.py:224
@@ -362,6 +367,7 @@ int uavsim_default_config(uavsim_config* c) {
     c->gps_sigma = 0.0;
     c->wind_drift = 0.0;
     c->latency_steps = 0;
+    c->gps_in_observation = 0;
     c->reserved2 = 0;
     return UAVSIM_OK;
 }
@@ -682,6 +688,8 @@ static Buffers range_buffers(const uavsim_handle* h, int e0, int n) {
     if (b.dwell_draws) b.dwell_draws += k * P;
     if (b.step_env_draws) b.step_env_draws += k * 4;
     if (b.reset_env_draws) b.reset_env_draws += k * 4;
+    if (b.env_sigma) b.env_sigma += k;
+    if (b.env_duty) b.env_duty += k;
     return b;
 }
 
@@ -715,6 +723,36 @@ int uavsim_step(uavsim_handle* h, const int32_t* actions, void* stream) {
                                                    : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "step_kernel launch");
     h->launches += step_launches(h);
+    return UAVSIM_OK;
+}
+
+int uavsim_step_ex(uavsim_handle* h, const int32_t* actions, const uint8_t* env_mask, uint32_t flags, void* stream) {
+    if (int rc = check_ready(h, false)) return rc;
+    if (!actions) return fail(UAVSIM_ERR_INVALID_ARG, "actions is NULL");
+    if (flags & ~UAVSIM_STEP_EXTRA) return fail(UAVSIM_ERR_INVALID_ARG, "unknown step flags");
+    if (h->frame_slot < 0) return fail(UAVSIM_ERR_STATE, "uavsim_reset has not been called");
+    const bool replay = h->cfg.rng_mode == UAVSIM_RNG_REPLAY, extra = (flags & UAVSIM_STEP_EXTRA) != 0;
+    h->buf.step_serial += 1;
+    const int next_slot = (h->frame_slot + 1) % ring_frames(h->cfg);
+    if (!extra) h->frame_slot = next_slot;  // a dropped repeat writes the row the commanded step is about to overwrite
+    h->buf.frame_slot = next_slot;
+    h->buf.step_mask = env_mask;
+    h->buf.extra_step = extra ? 1 : 0;
+    cudaError_t e = h->cfg.precision == UAVSIM_F64 ? launch_step_f64(h->p64, h->buf, actions, replay, (cudaStream_t)stream)
+                                                   : launch_step_f32(h->p32, h->buf, actions, replay, (cudaStream_t)stream);
+    const int n = step_launches(h);
+    h->buf.step_mask = nullptr;
+    h->buf.extra_step = 0;
+    h->buf.frame_slot = h->frame_slot;
+    if (e != cudaSuccess) return cuda_fail(e, "step_kernel launch");
+    h->launches += n;
+    return UAVSIM_OK;
+}
+
+int uavsim_set_env_params(uavsim_handle* h, const float* sigma_dev, const float* duty_dev) {
+    if (!h) return fail(UAVSIM_ERR_INVALID_ARG, "handle is NULL");
+    h->buf.env_sigma = sigma_dev;
+    h->buf.env_duty = duty_dev;
     return UAVSIM_OK;
 }
 

@@ -84,6 +84,7 @@ struct Params {
     int32_t relational, rel_dwell_steps, rel_min_cluster;  // RelationalUAVEnv wrapper (env_wrapper.py:47-62)
     Real rel_gamma, rel_dwell_bonus, rel_scale;
     Real gps_sigma;     // GPSNoisyEnv (sim_to_real_analysis.py:170-189), 0 = off
+    int32_t gps_in_obs; // PerturbedDQNEnv (sim_to_real_sweep.py:121-136): the noise moves the POSITION the observation pass sees
     double wind_drift;  // WindDriftEnv (:192-224), 0 = off
     int32_t frame_k, frame_mirror;  // frame ring: K = stack + latency frames; offset (floats) of the mirrored copy, 0 when K == 1
     int32_t frame_window, latency;  // VecFrameStack window k (the OLDEST k frames of the ring); LatencyEnv delay
@@ -123,6 +124,12 @@ struct Buffers {
     const double* dwell_draws;  // [E][P] relational wrapper's range probes (replay)
     const double* step_env_draws;   // [E][4] sim-to-real wrappers, step: gps_x, gps_y (replay)
     const double* reset_env_draws;  // [E][4] sim-to-real wrappers, reset: gps_x, gps_y, wind angle (replay)
+    // per-environment overrides of config.shadowing_std_db / duty_cycle (a whole robustness sweep in one batch), nullable
+    const float* env_sigma;         // [E] dB
+    const float* env_duty;          // [E] percent
+    // uavsim_step_ex: step only the envs whose mask byte is set / the PerturbedDQNEnv extra step (reward dropped)
+    const uint8_t* step_mask;
+    int32_t extra_step;
     // bookkeeping
     double* stat_sums;
     unsigned long long* error_word;  // min over (step_serial << 32 | env) of offending envs, ~0 = none
@@ -438,6 +445,7 @@ struct Draws {
     // whatever the sensor count, and the pair kernel (two environments per warp pass) issues it once.
     uint32_t pair_episode, pair_step;
     bool paired;
+    Real sigma;  // shadowing std of this environment (config.shadowing_std_db, or its per-env override)
 
     __device__ __forceinline__ Philox4 call(const Params<Real>& p, int lane, uint32_t c) const {
         return philox4x32_10(env_lo, env_hi | (kStreamStep << 24), episode, (step << 8) | ((uint32_t)lane << 3) | c,
@@ -462,12 +470,12 @@ struct Draws {
         } else {
             if constexpr (SPL == 2) {
                 const Philox4 q0 = call(p, lane, 0);
-                box_muller<Real>(q0.x, q0.y, p.sigma, d[0], e[0]);
-                box_muller<Real>(q0.z, q0.w, p.sigma, d[1], e[1]);
+                box_muller<Real>(q0.x, q0.y, sigma, d[0], e[0]);
+                box_muller<Real>(q0.z, q0.w, sigma, d[1], e[1]);
             } else {
                 const Philox4 q0 = paired ? pair_call(p, lane) : call(p, lane, 0);
                 const bool odd = paired && (env_lo & 1u);
-                box_muller<Real>(odd ? q0.z : q0.x, odd ? q0.w : q0.y, p.sigma, d[0], e[0]);
+                box_muller<Real>(odd ? q0.z : q0.x, odd ? q0.w : q0.y, sigma, d[0], e[0]);
             }
             if (exp) {
 #pragma unroll
@@ -491,11 +499,11 @@ struct Draws {
             }
         } else {
             const Philox4 q1 = call(p, lane, 1);
-            box_muller<Real>(q1.x, q1.y, p.sigma, a[0], b[0]);
+            box_muller<Real>(q1.x, q1.y, sigma, a[0], b[0]);
             if constexpr (SPL == 1) {
                 u[0] = u01<Real>(q1.z);
             } else {
-                box_muller<Real>(q1.z, q1.w, p.sigma, a[1], b[1]);
+                box_muller<Real>(q1.z, q1.w, sigma, a[1], b[1]);
                 const Philox4 q2 = call(p, lane, 2);
                 u[0] = u01<Real>(q2.x);
                 u[1] = u01<Real>(q2.y);
@@ -521,8 +529,8 @@ struct Draws {
         } else {
             const Philox4 q = call(p, lane, 3);
             Real unused;
-            box_muller<Real>(q.x, q.y, p.sigma, f[0], unused);
-            if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, p.sigma, f[1], unused);
+            box_muller<Real>(q.x, q.y, sigma, f[0], unused);
+            if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, sigma, f[1], unused);
         }
     }
     __device__ __forceinline__ Real winner(const Params<Real>& p, int lane, int k) const {
@@ -532,7 +540,7 @@ struct Draws {
         } else {
             const Philox4 q = call(p, lane, 4u + (uint32_t)k);
             Real c, unused;
-            box_muller<Real>(q.x, q.y, p.sigma, c, unused);
+            box_muller<Real>(q.x, q.y, sigma, c, unused);
             put(p, UAVSIM_SLOT_C, j, c);
             return c;
         }

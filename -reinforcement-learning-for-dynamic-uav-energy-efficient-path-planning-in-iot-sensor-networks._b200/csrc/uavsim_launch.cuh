@@ -92,6 +92,7 @@ inline bool lean_eligible(const Params<Real>& p, const Buffers& b, bool replay) 
     return false;
 #else
     return !std::is_same<Real, double>::value && !replay && !b.draw_export && !b.step_detail && !(p.gps_sigma > Real(0)) &&
+           !b.env_sigma && !b.env_duty && !b.step_mask && !b.extra_step &&
            !(p.wind_drift > 0.0) && ((p.fps == 3 && !p.relational) || (p.fps == 5 && p.relational && !p.domain_rand));
 #endif
 }

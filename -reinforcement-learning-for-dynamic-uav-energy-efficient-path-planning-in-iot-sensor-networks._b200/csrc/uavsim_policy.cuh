@@ -41,7 +41,7 @@ __device__ __forceinline__ int move_toward(float ux, float uy, float tx, float t
 // Shadowing draws of the agent's is_in_range probes: REPLAY reads the table [E][P], PHILOX its own stream.
 template <typename Real, bool REPLAY, int SPL>
 __device__ __forceinline__ void policy_probes(const Params<Real>& p, const uavsim_env_record* R, int e, int lane,
-                                              const double* __restrict__ probe_draws, Real (&g)[SPL]) {
+                                              const double* __restrict__ probe_draws, Real (&g)[SPL], Real sg) {
     if constexpr (REPLAY) {
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
@@ -53,8 +53,8 @@ __device__ __forceinline__ void policy_probes(const Params<Real>& p, const uavsi
         const Philox4 q = philox4x32_10((uint32_t)gid, ((uint32_t)(gid >> 32) & 0xffffffu) | (kStreamPolicy << 24),
                                         R->episode, ((uint32_t)R->step << 8) | ((uint32_t)lane << 3), p.keys);
         Real unused;
-        box_muller<Real>(q.x, q.y, p.sigma, g[0], unused);
-        if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, p.sigma, g[1], unused);
+        box_muller<Real>(q.x, q.y, sg, g[0], unused);
+        if constexpr (SPL == 2) box_muller<Real>(q.z, q.w, sg, g[1], unused);
     }
 }
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) nearest_greedy_kernel(const __grid_c
 
         // 1. any sensor with data in range?
         Real g[SPL];
-        policy_probes<Real, REPLAY, SPL>(p, R, e, lane, probe_draws, g);
+        policy_probes<Real, REPLAY, SPL>(p, R, e, lane, probe_draws, g, b.env_sigma ? (Real)b.env_sigma[e] : p.sigma);
         bool hit = false;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) hit |= s[k].active && s[k].buf > Real(0) && (s[k].det + g[k]) >= p.thr;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) max_throughput_greedy_kernel(const _
         load_sensors<Real, SPL>(b, p, e, N, lane, s);
         compute_det(p, ux, uy, s);
         Real g[SPL];
-        policy_probes<Real, REPLAY, SPL>(p, R, e, lane, probe_draws, g);
+        policy_probes<Real, REPLAY, SPL>(p, R, e, lane, probe_draws, g, b.env_sigma ? (Real)b.env_sigma[e] : p.sigma);
 
         const double battery_pct = R->battery / 274.0;  // :126 (hard-coded capacity)
         const int steps_left = p.max_steps - R->step;

@@ -126,6 +126,46 @@ __device__ __forceinline__ void write_info(const Params<Real>& p, int lane, cons
 // Per-environment draws of the sim-to-real wrappers (sim_to_real_analysis.py:176-181, :207): GPS noise pair for
 // the observation of `step` (0 = reset observation) and, at reset, the wind angle.  REPLAY: table [E][4];
 // PHILOX: stream kStreamMisc, counter word 3 = step << 8 | 4 (words 0, 1 there are the grid / inherited-SF draws).
+// The same pair as float64 (PerturbedDQNEnv adds it to the float64 copy of the position, sim_to_real_sweep.py:123-124).
+template <typename Real, bool REPLAY>
+__device__ __forceinline__ void env_draws_pos(const Params<Real>& p, const double* table, int e, uint32_t episode, uint32_t step,
+                                              double& gx, double& gy) {
+    if constexpr (REPLAY) {
+        gx = table ? table[4 * (size_t)e + 0] : 0.0;
+        gy = table ? table[4 * (size_t)e + 1] : 0.0;
+    } else {
+        const uint64_t gid = (uint64_t)(p.env_id_offset + e);
+        const Philox4 q = philox4x32_10((uint32_t)gid, ((uint32_t)(gid >> 32) & 0xffffffu) | (kStreamMisc << 24), episode,
+                                        (step << 8) | 4u, p.key0, p.key1);
+        Real z0, z1;
+        box_muller<Real>(q.x, q.y, p.gps_sigma, z0, z1);
+        gx = (double)z0;
+        gy = (double)z1;
+    }
+}
+// PerturbedDQNEnv._get_observation (sim_to_real_sweep.py:121-136): the position the observation pass sees.
+//   noisy = clip(float64(position) + N(0, sigma, 2), 0, [W-1, H-1]); obs[0], obs[1] = float32(noisy / [W, H]); the pass's
+//   RSSI takes float32(noisy) (iot_sensors.py:162).
+struct NoisyPos {
+    float x, y;    // float32(noisy): what calculate_rssi sees
+    float ox, oy;  // obs[0], obs[1]
+};
+template <typename Real>
+__device__ __forceinline__ NoisyPos noisy_position(float x, float y, int W, int H, double gx, double gy) {
+    const double nx = fmin(fmax((double)x + gx, 0.0), (double)(W - 1)), ny = fmin(fmax((double)y + gy, 0.0), (double)(H - 1));
+    NoisyPos n;
+    n.x = (float)nx;
+    n.y = (float)ny;
+    if constexpr (std::is_same<Real, double>::value) {
+        n.ox = (float)(nx / (double)W);
+        n.oy = (float)(ny / (double)H);
+    } else {
+        n.ox = __fdividef(n.x, (float)W);
+        n.oy = __fdividef(n.y, (float)H);
+    }
+    return n;
+}
+
 template <typename Real, bool REPLAY>
 __device__ __forceinline__ void env_draws(const Params<Real>& p, const double* table, int e, uint32_t episode, uint32_t step,
                                           float& gx, float& gy, double& angle) {
@@ -190,7 +230,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
                 const Real det0 = det_rssi(p, start_x, start_y, s0x, s0y);
                 const Philox4 q = philox4x32_10(env_lo, env_hi | (kStreamMisc << 24), episode, 1, p.key0, p.key1);
                 Real z0, z1;
-                box_muller<Real>(q.x, q.y, p.sigma, z0, z1);
+                box_muller<Real>(q.x, q.y, b.env_sigma ? (Real)b.env_sigma[e] : p.sigma, z0, z1);
                 Real ema = none_value<Real>();
                 int sf = p.init_sf;
                 adr_update(p, det0 + z0, ema, sf);
@@ -315,6 +355,7 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
     dr.step = 0;
     dr.paired = false;  // a reset observation belongs to one environment: (env, episode, step 0)
     dr.pair_episode = dr.pair_step = 0;
+    dr.sigma = b.env_sigma ? (Real)b.env_sigma[e] : p.sigma;
     dr.tab = REPLAY ? b.reset_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = exp;
     float* out = obs_frame(p, b, e);
@@ -323,9 +364,29 @@ __device__ __forceinline__ void reset_env(const Params<Real>& p, const Buffers& 
         for (int i = lane; i < p.obs_stride; i += 32) blk[i] = 0.0f;
         __syncwarp();
     }
+    NoisyPos np_{};
+    const bool gps_obs = p.gps_in_obs && p.gps_sigma > Real(0);
+    if (gps_obs) {  // PerturbedDQNEnv: reset() observes through the same noisy position (sim_to_real_sweep.py:121-136)
+        double gx, gy;
+        env_draws_pos<Real, REPLAY>(p, b.reset_env_draws, e, episode, 0u, gx, gy);
+        np_ = noisy_position<Real>(start_x, start_y, W, H, gx, gy);
+        h.x = np_.x;
+        h.y = np_.y;
+        compute_det(p, h.x, h.y, s);
+    }
     observe<Real, REPLAY, SPL, FPS, true, false>(p, h, s, dr, lane, out);
+    if (gps_obs) {
+        __syncwarp();
+        if (lane == 0) {
+            out[0] = np_.ox;
+            out[1] = np_.oy;
+        }
+        h.x = start_x;  // the true position is restored (:134)
+        h.y = start_y;
+        __syncwarp();
+    }
     double wind_angle = 0.0;
-    if (p.gps_sigma > Real(0) || p.wind_drift > 0.0) {  // GPSNoisyEnv.reset :183-185, WindDriftEnv.reset :205-210
+    if ((p.gps_sigma > Real(0) && !p.gps_in_obs) || p.wind_drift > 0.0) {  // GPSNoisyEnv.reset :183-185, WindDriftEnv.reset :205-210
         float gx, gy;
         double angle;
         env_draws<Real, REPLAY>(p, b.reset_env_draws, e, episode, 0u, gx, gy, angle);

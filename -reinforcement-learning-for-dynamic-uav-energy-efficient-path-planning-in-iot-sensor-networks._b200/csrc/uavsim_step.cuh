@@ -42,8 +42,16 @@ __device__ __forceinline__ bool feat_relational(const Params<Real>& p) {
     if constexpr (LEAN == kLeanRelational) return true; else if constexpr (LEAN != kGeneric) return false; else return p.relational != 0;
 }
 template <int LEAN, typename Real>
-__device__ __forceinline__ bool feat_gps(const Params<Real>& p) {
-    if constexpr (LEAN) return false; else return p.gps_sigma > Real(0);
+__device__ __forceinline__ bool feat_gps(const Params<Real>& p) {  // GPSNoisyEnv: noise added to the normalised obs[0], obs[1]
+    if constexpr (LEAN) return false; else return p.gps_sigma > Real(0) && !p.gps_in_obs;
+}
+template <int LEAN, typename Real>
+__device__ __forceinline__ bool feat_gps_obs(const Params<Real>& p) {  // PerturbedDQNEnv: noisy position inside the observation pass
+    if constexpr (LEAN) return false; else return p.gps_sigma > Real(0) && p.gps_in_obs;
+}
+template <int LEAN>
+__device__ __forceinline__ const float* feat_env_duty(const Buffers& b) {
+    if constexpr (LEAN) return nullptr; else return b.env_duty;
 }
 template <int LEAN, typename Real>
 __device__ __forceinline__ bool feat_wind(const Params<Real>& p) {
@@ -87,6 +95,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
         for (int k = 0; k < SPL; ++k) before[k] = (float)div_const(s[k].buf, p.rate, p.inv_rate);
     }
     const Real used = (Real)p.used_hover;                                      // uav.py:263, uav_env.py:530
+    const Real duty = feat_env_duty<LEAN>(b) ? (Real)(feat_env_duty<LEAN>(b)[e] / 100.0f) : p.duty_frac;
     // Phase 2: ADR update (draw A), link probability (draw B), duty-cycle gate (draw U)
     Real da[SPL], db[SPL], du[SPL];
     dr.collect(p, lane, da, db, du);
@@ -106,7 +115,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
                     const Real x = (rb - p.noise_floor) - required_snr_of<Real>(s[k].sf);
                     plink = 1.0 / (1.0 + exp(-x));
                 }
-                a = (plink * p.duty_frac) > du[k];
+                a = (plink * duty) > du[k];
             }
         } else {  // the same, straight-line: every lane computes, selects keep the state of lanes without data
             const bool has = s[k].active && s[k].buf > 0.f;
@@ -120,7 +129,7 @@ __device__ __forceinline__ void collect_action(const Params<Real>& p, const Buff
             const float rb = s[k].det + db[k];
             const float x = (rb - p.noise_floor) - required_snr_of<float>(sf2);
             const float plink = rb < p.thr ? 0.f : __fdividef(1.0f, 1.0f + __expf(-x));
-            a = has && (plink * p.duty_frac) > du[k];
+            a = has && (plink * duty) > du[k];
         }
         s[k].attempt = a;
         att[k] = __ballot_sync(kFull, a);
@@ -545,6 +554,10 @@ __device__ __forceinline__ Draws<Real, REPLAY, SPL> step_draws(const Params<Real
     dr.paired = SPL == 1;
     dr.pair_episode = ts.episode[k & ~1] - 1;
     dr.pair_step = (uint32_t)ts.step[k & ~1];
+    if constexpr (LEAN)
+        dr.sigma = p.sigma;
+    else
+        dr.sigma = b.env_sigma ? (Real)b.env_sigma[e] : p.sigma;
     dr.tab = REPLAY ? b.step_draws + (size_t)e * UAVSIM_NUM_SLOTS * p.P : nullptr;
     dr.exp = (!REPLAY && feat_draw_export<LEAN>(b))
                  ? reinterpret_cast<Real*>(feat_draw_export<LEAN>(b)) + (size_t)e * UAVSIM_NUM_SLOTS * p.P
@@ -675,6 +688,18 @@ __device__ __forceinline__ void sensor_phase(const Params<Real>& p, const Buffer
         h.battery = 0.0;
         h.vis_lo = collect ? ts.nvis_lo[k] : ts.vis_lo[k];  // relational rows carry the visited flag
         h.vis_hi = collect ? ts.nvis_hi[k] : ts.vis_hi[k];
+        if (feat_gps_obs<LEAN>(p)) {  // PerturbedDQNEnv._get_observation: the pass runs at the noisy position
+            double gx, gy;
+            env_draws_pos<Real, REPLAY>(p, b.step_env_draws, e, ts.episode[k] - 1, (uint32_t)ts.step[k], gx, gy);
+            const NoisyPos np_ = noisy_position<Real>(h.x, h.y, h.W, h.H, gx, gy);
+            h.x = np_.x;
+            h.y = np_.y;
+            compute_det(p, h.x, h.y, s);
+            if (lane == 0) {  // phase C writes obs[0], obs[1]: handed over in two fields only DomainRandEnv uses
+                ts.cur_dist[k] = np_.ox;
+                ts.jain[k] = (Real)np_.oy;
+            }
+        }
         observe<Real, REPLAY, SPL, FPS, false, STACK>(p, h, s, step_draws<Real, REPLAY, SPL, LEAN>(p, b, ts, k, e), lane,
                                                        obs_frame(p, b, e));
     }
@@ -878,7 +903,10 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             const int my_action = ts.action[tb][lane];
             ts.step[lane] = R.i32(kRStep) + 1;     // published for every slot: the even slot is its pair's clock
             ts.episode[lane] = R.w(kREpisode);
-            if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
+            bool masked_out = false;
+            if constexpr (!LEAN) masked_out = b.step_mask && !b.step_mask[e];  // uavsim_step_ex: this env sits the launch out
+            if (masked_out) {
+            } else if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
                 atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
                 if constexpr (kDeferredRestart) b.done[e] = 0;  // restart_kernel goes by the done flags of THIS step
             } else {
@@ -1139,7 +1167,9 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 R.set_f(kRElapsed, ts.elapsed[lane]);
                 R.set_i(kRStep, ts.step[lane]);
                 R.set_d(kRTotalReward, R.d(kRTotalReward) + (double)reward);
-                R.set_d(kREpReturn, R.d(kREpReturn) + (double)shaped);
+                bool extra = false;
+                if constexpr (!LEAN) extra = b.extra_step != 0;  // PerturbedDQNEnv's wind repeat: its reward is dropped (:119)
+                if (!extra) R.set_d(kREpReturn, R.d(kREpReturn) + (double)shaped);
                 R.set_f(kRLastBytes, (float)total_bytes);
                 if (flags & kFlagEdge) R.set_i(kREdge, R.i32(kREdge) + 1);
                 if (!collect) {
@@ -1153,7 +1183,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                     R.set_i(kRDelivered, R.i32(kRDelivered) + ((counts >> 12) & 0xf));
                 }
                 // outputs
-                restart = truncated && p.auto_reset;
+                restart = truncated && p.auto_reset && !extra;  // the commanded step that follows ends the episode
                 reinterpret_cast<Real*>(b.reward)[e] = shaped;
                 b.done[e] = truncated ? 1 : 0;
                 float* o = obs_frame(p, b, e);  // uav_env.py:644
@@ -1170,6 +1200,10 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 if (feat_wind<LEAN>(p)) {  // :220-223: the observation reports the raw drifted position
                     f0 = x;
                     f1 = y;
+                }
+                if (feat_gps_obs<LEAN>(p)) {  // PerturbedDQNEnv: the noisy position of the observation pass
+                    f0 = ts.cur_dist[lane];
+                    f1 = (float)ts.jain[lane];
                 }
                 if (feat_gps<LEAN>(p)) {   // GPSNoisyEnv._add_gps_noise, :176-181
                     float gx, gy;

@@ -106,6 +106,7 @@ class UAVVecEnv(_VecEnvBase):
                  max_sensors: Optional[int] = None, obs_slots: Optional[int] = None, n_stack: int = 1,
                  domain_randomisation=False, curriculum_stage=0, relational=False,
                  gps_sigma=0.0, wind_drift=0.0, latency_steps=0,
+                 shadowing_std_db=4.0, gps_in_observation=False, wind_extra_step=0.0,
                  precision="f32", rng="philox", seed=0, env_id_offset=0, auto_reset=True,
                  device="cuda:0", step_detail=False, export_draws=False, action_mask=True,
                  terminal_info: Optional[bool] = None, info_every_step=False):
@@ -165,6 +166,12 @@ class UAVVecEnv(_VecEnvBase):
         cfg.gps_sigma = float(gps_sigma)      # sim_to_real_analysis.py:170-189
         cfg.wind_drift = float(wind_drift)    # sim_to_real_analysis.py:192-224
         cfg.latency_steps = int(latency_steps)  # sim_to_real_analysis.py:227-245
+        # PerturbedDQNEnv of the sim-to-real sweep (sim_to_real_sweep.py:107-139): shadowing sigma of every sensor, GPS noise
+        # inside the observation pass, and (host side, `wind_extra_step`) the probabilistic repeat of a move
+        cfg.shadowing_std_db = float(shadowing_std_db)
+        cfg.gps_in_observation = int(bool(gps_in_observation))
+        self.wind_extra_step = float(wind_extra_step)
+        self._wind_rng = None
         self.latency_steps = int(latency_steps)
         self._stage = -1
         self.cfg = cfg
@@ -359,9 +366,38 @@ class UAVVecEnv(_VecEnvBase):
         invalid actions are reported by `poll_errors()`."""
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        if self.wind_extra_step > 0 and self.cfg.rng_mode == N.RNG_PHILOX:
+            self._wind_repeat(actions)
         with torch.cuda.device(self.device):
             N.check(self.lib.uavsim_step(self._h, _ptr(actions), self._stream()))
         return self.obs, self.reward, self.done
+
+    def _wind_repeat(self, actions: torch.Tensor) -> None:
+        """PerturbedDQNEnv.step (sim_to_real_sweep.py:117-119): with probability min(0.95, wind / 2) a move action is
+        run once more first and that extra step's result is dropped."""
+        if self._wind_rng is None:
+            self._wind_rng = torch.Generator(device=self.device)
+            self._wind_rng.manual_seed(int(self.cfg.seed) ^ 0x57494E44)
+        p_extra = min(0.95, self.wind_extra_step / 2.0)
+        mask = ((torch.rand(self.num_envs, device=self.device, generator=self._wind_rng) < p_extra) & (actions < 4)).to(torch.uint8)
+        self.step_extra_tensors(actions, mask)
+
+    def step_extra_tensors(self, actions: torch.Tensor, env_mask: torch.Tensor) -> None:
+        """The dropped repeat itself (uavsim_step_ex with UAVSIM_STEP_EXTRA) for the envs whose mask byte is set; the
+        commanded step must follow.  Replay-mode callers bind the repeat's own draw tables before this call."""
+        m = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.uavsim_step_ex(self._h, _ptr(actions), _ptr(m), N.STEP_EXTRA, self._stream()))
+
+    def set_env_params(self, shadowing_std_db=None, duty_cycle=None) -> None:
+        """Per-environment shadowing sigma (dB) / duty cycle (percent) columns (uavsim_set_env_params): one batch can
+        hold a whole robustness sweep (sim_to_real_sweep.py:72-77 varies them per run).  None = the handle's value."""
+        def col(a):
+            return None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float32)).to(self.device).contiguous()
+        self._env_sigma, self._env_duty = col(shadowing_std_db), col(duty_cycle)
+        for t in (self._env_sigma, self._env_duty):
+            assert t is None or tuple(t.shape) == (self.num_envs,)
+        N.check(self.lib.uavsim_set_env_params(self._h, _ptr(self._env_sigma), _ptr(self._env_duty)))
 
     def make_host_buffers(self):
         """Pinned host buffers for `step_host` (actions in; obs, reward, done out), allocated NUMA-local to the GPU:
@@ -552,6 +588,9 @@ class UAVVecEnv(_VecEnvBase):
         host = self._np_host
         host["actions"].copy_(self._pending_actions)
         self._pending_actions = None
+        if self.wind_extra_step > 0 and self.cfg.rng_mode == N.RNG_PHILOX:
+            self._actions_dev.copy_(host["actions"], non_blocking=True)
+            self._wind_repeat(self._actions_dev)
         with torch.cuda.device(self.device):
             N.check(self.lib.uavsim_step_host(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
                                               _ptr(host["done"]), self._stream()))

@@ -130,7 +130,12 @@ typedef struct uavsim_config {
     int32_t grids[UAVSIM_MAX_GRIDS][2];
     double min_start_dist;               /* 50 */
     int32_t max_start_tries;             /* 200 */
-    int32_t reserved1;
+    int32_t gps_in_observation;          /* with gps_sigma > 0: 0 = GPSNoisyEnv (noise added to the normalised obs[0], obs[1],
+                                            sim_to_real_analysis.py:176-181); 1 = PerturbedDQNEnv of the sweep
+                                            (sim_to_real_sweep.py:121-136): the noise, in cells, moves the POSITION the
+                                            observation pass sees -- clipped to the grid; obs[0], obs[1] report it and the
+                                            pass's ADR update / range check run at it; the true position is untouched.
+                                            Needs reset_mode FIXED and no wrapper. */
     double prox_eta;                     /* 2.0 */
     double jain_bonus;                   /* 0.5: reward += jain_bonus*(J-0.5)/N */
 
@@ -350,6 +355,18 @@ int uavsim_step_host(uavsim_handle* h, const int32_t* actions_host, float* obs_h
                      uint8_t* done_host, void* stream);
 /* Number of env ranges uavsim_step_host pipelines over: 1 (no overlap), 2, 4 or 8. */
 int uavsim_set_host_chunks(uavsim_handle* h, int32_t chunks);
+
+/* uavsim_step for a SUBSET of the envs, and PerturbedDQNEnv's wind repeat (sim_to_real_sweep.py:117-119: "with
+ * probability min(0.95, wind / 2) a move is run once more first, and that extra step's result is dropped").
+ * env_mask_dev: [E] bytes, only envs with a non-zero byte step (NULL = all).  flags: */
+#define UAVSIM_STEP_EXTRA 1u /* the launch is such a dropped repeat: no episode restarts, the reward does not enter
+                                episode_return (it does enter total_reward, as env.total_reward in the reference), the
+                                frame ring does not advance -- the commanded step that follows overwrites reward / done
+                                / observation and ends the episode if the repeat exhausted it */
+int uavsim_step_ex(uavsim_handle* h, const int32_t* actions_dev, const uint8_t* env_mask_dev, uint32_t flags, void* stream);
+/* Per-environment overrides of config.shadowing_std_db (dB) and config.duty_cycle (percent): a whole robustness sweep
+ * (sim_to_real_sweep.py:72-77 varies them per run) in one batch.  [E] float32 device arrays, borrowed; NULL = config. */
+int uavsim_set_env_params(uavsim_handle* h, const float* shadowing_std_db_dev, const float* duty_cycle_dev);
 
 /* ---- on-device heuristic driver ------------------------------- */
 /* NearestSensorGreedy.select_action for every env (greedy_agents.py:73-100, :41-68): COLLECT if a sensor with

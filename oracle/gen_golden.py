@@ -355,11 +355,88 @@ def generate_sim_to_real(name):
     print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
 
 
+# --------------------------------------------------------------------------
+# PerturbedDQNEnv of the sim-to-real sweep (sim_to_real_sweep.py:107-139 on AnalysisUAVEnv, compare_agents.py:62-147):
+# per-sensor shadowing sigma, GPS noise applied to the position inside the observation pass, probabilistic extra step
+# for wind.  One fixture = chained episodes; every INNER env step is stored (flag `is_extra` marks the wind repeats),
+# with its slot draws, the GPS pair drawn inside its observation ("extra") and the wind gate's uniform ("pre").
+# --------------------------------------------------------------------------
+PERT_SCENARIOS = {
+    "pert_gps10_200_n20": dict(gps_sigma=10.0, shadow_sigma=4.0, wind_drift=0.0, seed=41, steps=200, p_collect=0.35, max_steps=90),
+    "pert_shadow8_200_n20": dict(gps_sigma=0.0, shadow_sigma=8.0, wind_drift=0.0, seed=42, steps=200, p_collect=0.5, max_steps=90),
+    "pert_wind1_200_n20": dict(gps_sigma=0.0, shadow_sigma=4.0, wind_drift=1.0, seed=43, steps=220, p_collect=0.3, max_steps=120),
+    "pert_all_200_n20": dict(gps_sigma=5.0, shadow_sigma=6.0, wind_drift=2.0, seed=44, steps=220, p_collect=0.35, max_steps=150),
+}
+PERT_KEYS = ("reward", "truncated", "pos", "battery", "sf", "visited", "obs", "buf", "tx", "lost", "ema", "draws", "extra", "pre",
+             "total_reward", "boundary_hits", "edge_steps", "step")
+PERT_INFO = ("coverage_percentage", "total_reward", "boundary_hits", "edge_steps", "total_data_collected", "battery")
+
+
+def generate_perturbed(name):
+    import random
+    sc = PERT_SCENARIOS[name]
+    H.load_reference()
+    H.REC.normalise = True
+    make, npx = H.load_perturbed_dqn_env()
+    grid, n = (200, 200), 20                     # sim_to_real_sweep.py:68-69
+    Env = make(sc["gps_sigma"], sc["shadow_sigma"], sc["wind_drift"])
+    random.seed(sc["seed"])                      # run_dqn_episode, sim_to_real_sweep.py:198-205
+    np.random.seed(sc["seed"])
+    layout = np.random.uniform([0, 0], list(grid), (n, 2))       # what the constructor is about to draw
+    np.random.seed(sc["seed"])
+    env = Env(max_sensors_limit=50, grid_size=grid, num_sensors=n, max_steps=sc["max_steps"], path_loss_exponent=3.8,
+              rssi_threshold=-85.0, sensor_duty_cycle=10.0, uav_start_position=(0, 0))
+    assert np.array_equal(np.array(env.sensor_positions, dtype=np.float32), layout.astype(np.float32))
+    rng = np.random.default_rng(sc["seed"])
+    blob, ep, inner, outer_actions = {}, 0, [], []
+    env.reset(seed=sc["seed"])
+    first = env.inner_reset
+    for t in range(sc["steps"]):
+        a = 4 if rng.random() < sc["p_collect"] else int(rng.integers(0, 4))
+        env.inner = []
+        obs, r, term, trunc, info = env.step(a)
+        for i, st in enumerate(env.inner):
+            st = dict(st)
+            st["is_extra"] = np.bool_(i < len(env.inner) - 1)
+            st["action"] = np.int8(a)
+            st.pop("info", None)
+            inner.append(st)
+        outer_actions.append(a)
+        if trunc or t == sc["steps"] - 1:
+            S = H.stack_steps(inner)
+            for k in PERT_KEYS + ("is_extra", "action"):
+                blob["e%d/%s" % (ep, k)] = S[k]
+            for k in ("obs", "draws", "fill", "sf", "ema", "buf", "extra", "pos"):
+                blob["e%d/reset_%s" % (ep, k)] = first[k]
+            blob["e%d/last_info" % ep] = np.array([float(info[k]) for k in PERT_INFO])
+            blob["e%d/last_ratios" % ep] = np.array(info["sensor_collection_ratios"], dtype=np.float64)
+            blob["e%d/wrapper_steps" % ep] = np.int32(len(outer_actions))
+            ep, inner, outer_actions = ep + 1, [], []
+            if trunc:
+                env.reset()                       # DummyVecEnv: reset right after the terminal step
+                first = env.inner_reset
+    meta = dict(name=name, flavour="norm", cls="PerturbedDQNEnv", gps_sigma=sc["gps_sigma"], shadow_sigma=sc["shadow_sigma"],
+                wind_drift=sc["wind_drift"], grid=list(grid), n=n, start=[0.0, 0.0], episodes=ep, seed=sc["seed"],
+                env_kwargs=dict(max_steps=sc["max_steps"]), info_keys=list(PERT_INFO),
+                numpy=np.__version__, python=platform.python_version(), generator="oracle/gen_golden.py",
+                reference_entry="src/agents/dqn/dqn_evaluation_results/sim_to_real_sweep.py::_perturb_positions_dqn "
+                                "(exec'd slice) over compare_agents.py::AnalysisUAVEnv (exec'd slice)")
+    blob["positions"] = layout.astype(np.float32)
+    blob["meta"] = np.array(json.dumps(meta))
+    path = OUT / ("%s.norm.npz" % name)
+    np.savez_compressed(path, **blob)
+    print("%-36s norm %7.1f kB  episodes=%d" % (name, path.stat().st_size / 1e3, ep))
+
+
 RAW_TOO = ("c1_greedy_500_n20",)
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS) + list(REL_SCENARIOS) + list(S2R_SCENARIOS))
+    names = sys.argv[1:] or (list(SCENARIOS) + list(DR_SCENARIOS) + list(REL_SCENARIOS) + list(S2R_SCENARIOS) +
+                             list(PERT_SCENARIOS))
     for nm in names:
+        if nm in PERT_SCENARIOS:
+            generate_perturbed(nm)
+            continue
         if nm in S2R_SCENARIOS:
             generate_sim_to_real(nm)
             continue

@@ -569,3 +569,105 @@ def s2r_traced_step(env, npx, action):
     st = traced_step(env, action)
     st["extra"] = np.array(npx.extra + [np.nan] * (4 - len(npx.extra)), dtype=np.float64)
     return st
+
+
+# --------------------------------------------------------------------------
+# PerturbedDQNEnv of the sim-to-real SWEEP (src/agents/dqn/dqn_evaluation_results/sim_to_real_sweep.py:107-139) on top
+# of AnalysisUAVEnv (compare_agents.py:62-147): per-sensor shadowing sigma, GPS noise applied to the position INSIDE
+# the observation pass (so the pass's ADR update and range check see the noisy position), and a probabilistic extra
+# whole step for wind.
+# --------------------------------------------------------------------------
+class _SweepNumpyProxy(_ExtraNumpyProxy):
+    """`np` inside the exec'd `_perturb_positions_dqn`: records the wrapper's own draws -- np.random.random() (the wind
+    gate) and np.random.normal(0, sigma, size=2) (the GPS noise pair) -- in call order."""
+
+    class _Random(_ExtraNumpyProxy._Random):
+        def normal(self, *a, **k):
+            v = self._real.normal(*a, **k)
+            self._owner.extra.extend(float(x) for x in np.atleast_1d(v))
+            return v
+
+        def random(self, *a, **k):
+            v = self._real.random(*a, **k)
+            self._owner.extra.append(float(v))
+            return v
+
+    def __init__(self, real):
+        super().__init__(real)
+        self.random = self._Random(real.random, self)
+
+
+def load_perturbed_dqn_env():
+    """Returns (make(gps_sigma, shadow_sigma, wind_drift, ple) -> PerturbedDQNEnv class, numpy proxy).  The class text
+    of AnalysisUAVEnv and of `_perturb_positions_dqn` is exec'd unchanged; the base handed to the factory is a TRACING
+    subclass of AnalysisUAVEnv whose step / reset record each INNER env step (draw table, state, padded observation)
+    in `env.inner` -- PerturbedDQNEnv.step may run two of them."""
+    mods = load_reference()
+    if "pert_make" in mods:
+        return mods["pert_make"], mods["pert_np"]
+    import gymnasium
+    base = REFERENCE_ROOT / "src" / "agents" / "dqn" / "dqn_evaluation_results"
+    lines = (base / "compare_agents.py").read_text().splitlines()
+    a = next(i for i, l in enumerate(lines) if l.startswith("class AnalysisUAVEnv"))
+    z = next(i for i, l in enumerate(lines) if "TRAJECTORY TRACKING" in l)
+    ns_a = {"__name__": "compare_agents_slice", "np": np, "gymnasium": gymnasium, "UAVEnvironment": mods["UAVEnvironment"]}
+    exec(compile("\n" * a + "\n".join(lines[a:z]), str(base / "compare_agents.py"), "exec"), ns_a)
+    Analysis = ns_a["AnalysisUAVEnv"]
+    proxy = _SweepNumpyProxy(np)
+
+    class TracingAnalysisEnv(Analysis):
+        def __init__(self, **kw):
+            self.inner = []
+            super().__init__(**kw)
+
+        def _trace(self, out, reward=None, truncated=None, pre=()):
+            st = snapshot(self)
+            st["obs"] = np.asarray(out, dtype=np.float32)
+            st["draws"] = REC.draws[:6].copy()
+            ex = list(proxy.extra)                       # the GPS pair drawn inside this inner step's observation
+            st["extra"] = np.array(ex + [np.nan] * (2 - len(ex)), dtype=np.float64)
+            st["pre"] = np.array(list(pre) + [np.nan] * (1 - len(pre)), dtype=np.float64)   # the wind gate's uniform
+            proxy.extra.clear()
+            if reward is not None:
+                st["reward"] = np.float64(reward)
+                st["truncated"] = np.bool_(truncated)
+            return st
+
+        def reset(self, **kw):
+            proxy.extra.clear()
+            REC.fill = []
+            REC.begin(self.num_sensors)
+            try:
+                obs, info = super().reset(**kw)
+            finally:
+                REC.end()
+            st = self._trace(obs)
+            st["fill"] = np.array(REC.fill, dtype=np.float64)
+            self.inner_reset = st
+            self.inner = []
+            return obs, info
+
+        def step(self, action):
+            pre = list(proxy.extra)
+            proxy.extra.clear()
+            REC.begin(self.num_sensors)
+            try:
+                out = super().step(action)
+            finally:
+                REC.end()
+            st = self._trace(out[0], out[1], out[3], pre)
+            st["info"] = out[4]
+            self.inner.append(st)
+            return out
+
+    path = base / "sim_to_real_sweep.py"
+    lines = path.read_text().splitlines()
+    a = next(i for i, l in enumerate(lines) if l.startswith("def _perturb_positions_dqn"))
+    z = next(i for i, l in enumerate(lines) if l.startswith("def _perturb_positions_rel"))
+    ns = {"__name__": "sim_to_real_sweep_slice", "np": proxy}
+    exec(compile("\n" * a + "\n".join(lines[a:z]), str(path), "exec"), ns)
+
+    def make(gps_sigma, shadow_sigma, wind_drift, ple=3.8):
+        return ns["_perturb_positions_dqn"](TracingAnalysisEnv, gps_sigma, shadow_sigma, wind_drift, ple)
+    mods["pert_make"], mods["pert_np"] = make, proxy
+    return make, proxy

@@ -739,6 +739,70 @@ class SimToRealOracle:
         return obs, reward, terminated, truncated
 
 
+class PerturbedOracle:
+    """PerturbedDQNEnv of the sim-to-real sweep (sim_to_real_sweep.py:107-139) over AnalysisUAVEnv's zero padding
+    (compare_agents.py:62-147), restated:
+      shadow_sigma : every sensor's shadowing_std_db (:112-115) -- the base env's draw source is built with it
+      gps_sigma    : _get_observation (:121-136) replaces uav.position by clip(position + N(0, sigma, size=2), 0,
+                     [W-1, H-1]) (a float64 array) for the duration of the pass: obs[0], obs[1] report the noisy
+                     position and the pass's ADR update / range check use it (cast to float32 by calculate_rssi,
+                     iot_sensors.py:162); the true position is restored afterwards.  Applies to reset() too.
+      wind_drift   : step (:117-119): for a move action, with probability min(0.95, wind / 2) (np.random.random(),
+                     the global legacy stream) one EXTRA whole env step with the same action runs first; its reward
+                     and observation are dropped, its effects on the state (and env.total_reward) stay.
+    The wrapper's own draws come from the global legacy numpy stream; `extra` / `pre` record them like the fixtures
+    (`source(kind, a, b)` replays recorded values instead)."""
+
+    def __init__(self, env: "OracleEnv", gps_sigma=0.0, wind_drift=0.0, obs_slots=50, source=None):
+        self.env, self.gps_sigma, self.wind_drift = env, float(gps_sigma), float(wind_drift)
+        fps = 5 if env.p["include_sensor_positions"] else 3
+        self.pad = (obs_slots - env.n) * fps
+        self.source = source or (lambda kind, a, b: getattr(np.random, kind)(a, b) if kind != "random" else np.random.random())
+        self.extra, self.pre, self.inner = [], [], []
+        self._plain_obs = env.observation
+        env.observation = self._observation          # OracleEnv.step / reset call self.observation()
+
+    def _observation(self):
+        env = self.env
+        if self.gps_sigma <= 0:
+            return self._plain_obs()
+        true_pos = env.pos
+        gx = float(self.source("normal", 0, self.gps_sigma))
+        gy = float(self.source("normal", 0, self.gps_sigma))
+        self.extra += [gx, gy]
+        noisy = np.array([float(true_pos[0]) + gx, float(true_pos[1]) + gy], dtype=np.float64)
+        env.pos = np.clip(noisy, 0, [env.W - 1, env.H - 1])
+        try:
+            return self._plain_obs()
+        finally:
+            env.pos = true_pos
+
+    def _pad(self, raw):
+        return np.concatenate([raw, np.zeros(self.pad, dtype=np.float32)]).astype(np.float32)
+
+    def reset(self, fill):
+        self.extra, self.pre = [], []
+        return self._pad(self.env.reset(fill))
+
+    def step(self, action):
+        """Returns (padded obs, reward, terminated, truncated); self.inner lists the inner steps it ran as
+        (obs, reward, truncated, extra, pre) tuples."""
+        self.inner = []
+        pre = []
+        if self.wind_drift > 0 and action in (0, 1, 2, 3):
+            u = float(self.source("random", 0, 1))
+            pre = [u]
+            if u < min(0.95, self.wind_drift / 2.0):
+                self.extra = []
+                o, r, te, tr = self.env.step(action)
+                self.inner.append((self._pad(o), r, tr, list(self.extra), pre))
+                pre = []
+        self.extra = []
+        o, r, te, tr = self.env.step(action)
+        self.inner.append((self._pad(o), r, tr, list(self.extra), pre))
+        return self._pad(o), r, te, tr
+
+
 COLLECT_KEYS = ("bytes_collected", "was_new_sensor", "was_empty", "all_sensors_collected",
                 "battery_used", "collision_count", "data_loss", "urgency_reduced",
                 "sensor_urgency")

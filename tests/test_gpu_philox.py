@@ -95,59 +95,6 @@ def test_exported_draws_match_independent_philox(pkg, N):
     env.close()
 
 
-@pytest.mark.parametrize("N", [20, 50])
-def test_packed_kernel_draws_match_independent_philox(pkg, N):
-    """The float32 production kernel (uavsim_packed.cuh) addresses its step draws per sensor PAIR: counter =
-    (env id, stream 7 | env hi, episode, step << 8 | pair << 2 | call); call 0 -> D, E of the even (x, y) and odd
-    (z, w) sensor, call 1 -> A, B likewise, call 2 -> U of both (x, y) and the pair's C draws (Box-Muller of z, w)."""
-    import torch
-    E, seed, off = 64, 0xBADC0DE77, 4096
-    env = pkg.UAVVecEnv(E, grid_size=(60, 60), num_sensors=N, precision="f32", rng="philox", seed=seed,
-                        env_id_offset=off, auto_reset=False, export_draws=True, uav_start_position=(30.0, 30.0),
-                        sensor_duty_cycle=100.0)
-    env.reset_tensors()
-    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
-    NP = (N + 1) // 2
-    pairs = np.arange(NP, dtype=np.uint64)
-    envs = np.broadcast_to((np.arange(E, dtype=np.uint64) + np.uint64(off))[:, None], (E, NP))
-    c1 = np.full((E, NP), 7 << 24, dtype=np.uint64)
-    episode = np.zeros((E, NP), dtype=np.uint64)
-
-    def inter(even, odd):
-        return np.stack([even, odd], axis=2).reshape(E, 2 * NP)[:, :N]
-
-    saw_c = 0
-    for t, a in enumerate([4, 0, 4, 3, 4], start=1):
-        env.step_tensors(torch.full((E,), a, dtype=torch.int32, device=env.device))
-        exp = env.draw_export.cpu().numpy().astype(np.float64)             # [E, 6, N]
-
-        def call(c):
-            c3 = (np.uint64(t) << np.uint64(8)) | (pairs[None, :] << np.uint64(2)) | np.uint64(c)
-            return philox4x32_10(envs, c1, episode, np.broadcast_to(c3, (E, NP)), k0, k1)
-        q0 = call(0)
-        d0, e0 = box_muller(q0[0], q0[1], 4.0)
-        d1, e1 = box_muller(q0[2], q0[3], 4.0)
-        np.testing.assert_allclose(exp[:, 4, :], inter(d0, d1), rtol=2e-4, atol=2e-4)      # float32 MUFU Box-Muller
-        np.testing.assert_allclose(exp[:, 5, :], inter(e0, e1), rtol=2e-4, atol=2e-4)
-        if a == 4:
-            q1, q2 = call(1), call(2)
-            a0, b0 = box_muller(q1[0], q1[1], 4.0)
-            a1, b1 = box_muller(q1[2], q1[3], 4.0)
-            np.testing.assert_allclose(exp[:, 0, :], inter(a0, a1), rtol=2e-4, atol=2e-4)
-            np.testing.assert_allclose(exp[:, 1, :], inter(b0, b1), rtol=2e-4, atol=2e-4)
-            u = inter((q2[0].astype(np.float64) + 0.5) * 2.0 ** -32, (q2[1].astype(np.float64) + 0.5) * 2.0 ** -32)
-            np.testing.assert_allclose(exp[:, 2, :], u, rtol=1e-6, atol=1e-7)
-            cc0, cc1 = box_muller(q2[2], q2[3], 4.0)
-            c = inter(cc0, cc1)
-            got = ~np.isnan(env.draw_export.cpu().numpy()[:, 3, :])
-            saw_c += int(got.sum())
-            np.testing.assert_allclose(exp[:, 3, :][got], c[got], rtol=2e-4, atol=2e-4)
-        else:
-            assert np.isnan(env.draw_export.cpu().numpy()[:, :4, :]).all()          # move steps draw only D and E
-    assert saw_c > 0                                                                 # winners drew their range check
-    env.close()
-
-
 def test_float32_draw_statistics(pkg):
     import torch
     E, N = 8192, 50

@@ -46,11 +46,26 @@ def _fingerprint() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Builds (or reuses) the library.  Safe under `torch.distributed.run`, where every rank imports the package at
+    once: one process builds under an exclusive file lock, the others wait for it and find the fingerprint fresh; the
+    library is linked under a temporary name and renamed into place, so nobody can dlopen a half-written file."""
+    import fcntl
     stamp = OBJ / "fingerprint"
     fp = _fingerprint()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
         return LIB
     OBJ.mkdir(exist_ok=True)
+    with open(OBJ / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
+                return LIB                      # another rank built it while this one waited
+            return _build_locked(fp, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(fp: str, stamp: Path, verbose: bool) -> Path:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -68,10 +83,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-    link = [nvcc, *ARCH, "-shared", "-o", str(LIB), *objs]
+    tmp = LIB.with_name(LIB.name + ".tmp%d" % os.getpid())
+    link = [nvcc, *ARCH, "-shared", "-o", str(tmp), *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)
     stamp.write_text(fp)
     return LIB
 

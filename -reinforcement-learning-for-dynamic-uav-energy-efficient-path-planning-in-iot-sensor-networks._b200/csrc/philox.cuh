@@ -7,7 +7,9 @@
 // independently by a million environments, so the batched simulator addresses each draw by
 // a counter instead of by its position in a stream:
 //     key     = (seed_lo, seed_hi)
-//     counter = (global env id, stream id | hi env bits, episode, step << 7 | sensor << 1 | call)
+//     counter = (global env id, stream id | hi env bits, episode, step << 8 | lane << 3 | call)
+// (sensor j sits in lane j % 32, slot j / 32 of a call's four words; P <= 32: the observation draws of a step are keyed
+// by the even / odd environment PAIR instead, stream kStreamPair -- see Draws in uavsim_device.cuh)
 // A draw therefore depends only on (seed, env id, episode, step, sensor, slot) -- not on how
 // environments are sharded over GPUs, not on launch geometry, not on other environments.
 #pragma once

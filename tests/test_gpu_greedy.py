@@ -43,7 +43,7 @@ def test_config1_greedy_rollouts_on_device(pkg):
     import torch
     from golden_util import Fixture
     fx = Fixture("c1_greedy_500_n20")
-    seeds = fx.seeds[:10]
+    seeds = fx.seeds                                 # all 20 episodes of BASELINE configs[0]
     R = [_oracle_rollout(fx, s) for s in seeds]
     gold = [fx.ep(s) for s in seeds]
     for r, g in zip(R, gold):                       # the oracle rollout IS the reference's rollout

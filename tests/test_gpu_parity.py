@@ -186,6 +186,28 @@ def test_float32_throughput_build_against_the_oracle(pkg, name):
         assert res["dones"] >= 0.9 * kw["E"], res
 
 
+def test_config3_full_size_domain_rand_against_the_oracle(pkg):
+    """BASELINE configs[2] at FULL size: 65,536 DomainRandEnv environments, N = 10..50 padded to 50 observation slots,
+    scenarios (grid, layout, far start, inherited SF) drawn in-kernel with Philox, float32 throughput build.  The oracle
+    replays the exported draws of EVERY environment (not a sample); the production (LEAN) handle runs alongside and
+    must agree bit for bit."""
+    from parity_util import run_parity_case
+    rng = np.random.default_rng(7)
+    E = 65536
+    n = rng.integers(10, 51, size=E)
+    res = run_parity_case(pkg, E=E, N=50, P=50, per_env_n=n, grid=(500, 500), steps=20, seed=71, p_collect=0.3,
+                          precision="f32", margin_aware=True, start="random", domain_rand=True, obs_slots=50,
+                          draws="philox", lean_twin=True, ref_kwargs=dict(curriculum_stage=4))
+    sensor_steps = int(n.sum()) * 20
+    print("\n[configs[2] full size] %d sensor-steps, %d justified flips, per-key %s, reward/scale %.2e" %
+          (sensor_steps, res["flips"], {k: "%.1e" % v for k, v in res["per_key"].items()}, res["reward_abs_over_scale"]))
+    assert res["unmargined_flips"] == 0 and res["discrete_mismatches"] == 0, (res.get("flip_names", [])[:8], res["first_bad"])
+    assert res["flips"] <= 4e-6 * sensor_steps + 4
+    for k in ("obs", "ema", "buf", "tx", "lost", "reward", "prev_dist"):
+        assert res["per_key"][k] <= FLOAT_TOL, (k, res["per_key"])
+    assert res["reward_abs_over_scale"] <= FLOAT_TOL and res["lean_twin_steps"] == 20
+
+
 def test_config2_full_episodes_to_truncation(pkg):
     """configs[1] over WHOLE episodes: 1024 envs, uniform random actions until every env has truncated
     (battery-limited, ~1790 steps) and restarted in-kernel; state compared every 64 steps."""

@@ -114,7 +114,7 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
             Buffers bb;
 #define UAVSIM_LAUNCH_LEAN(S, F, MODE, PAIRED)                                                                   \
     do {                                                                                                      \
-        constexpr size_t smem = step_smem_bytes<Real, S, PAIRED>();                                           \
+        constexpr size_t smem = step_smem_bytes<Real, S, PAIRED, true>();                                     \
         constexpr int warps = step_warps<Real, S, PAIRED>();                                                  \
         auto k = stack ? step_kernel<Real, false, S, F, true, MODE, PAIRED> : step_kernel<Real, false, S, F, false, MODE, PAIRED>; \
         launch_step_kernel(k, smem, warps, true, b, &grid, &bb);                                            \

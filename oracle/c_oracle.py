@@ -16,7 +16,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "_build" / "liboracle.so"
 MAXS = 64
 SLOTS = 6
-DETAIL_COUNT = 20   # 16 shared with the CUDA detail row + 4 oracle-only (margins, reward scale)
+DETAIL_COUNT = 21   # 16 shared with the CUDA detail row + 5 oracle-only (margins, reward scale)
 
 _PARAM_DOUBLES = (
     "data_generation_rate", "max_buffer_size", "rssi_threshold", "duty_cycle", "max_battery",

@@ -87,7 +87,9 @@ enum { D_COLLISIONS = 0, D_BYTES, D_URG_RED, D_MEAN_URG, D_WAS_NEW, D_WAS_EMPTY,
        D_MARGIN_BYTES = 18, /* min |buffer + new - max_buffer| over the saturation compares and |buffer - rate * dt|
                                over the drains (whether the buffer empties), in bytes */
        D_REWARD_SCALE = 19, /* sum of |term| over the terms the base reward was assembled from */
-       D_COUNT = 20 };
+       D_MARGIN_DIST = 20,  /* min |d - d_break| (metres) over the two-ray branch selections (iot_sensors.py:174-187): the
+                               two branches differ by 0.46 dB at the break, so the selection is a discrete decision */
+       D_COUNT = 21 };
 
 /* margin / scale accumulators of the env-step in flight (NULL = not recorded) */
 static __thread double* g_mg = NULL;
@@ -177,6 +179,7 @@ static double det_rssi(const orc_params* p, float ux, float uy, float sx, float 
     float d = sqrtf(g * g + alt2);
     float lg = (float)log10((double)d);
     double d_break = (4 * M_PI * 0.5 * p->altitude) / 0.345;
+    mg_note(D_MARGIN_DIST, (double)d, d_break);
     double pl;
     if ((double)d < d_break) {
         float t = 20.0f * lg;
@@ -542,7 +545,7 @@ int orc_step_env(const orc_params* p, orc_env* e, int action, const double* draw
     if (action < 0 || action > 4) return -1;
     if (detail) {
         for (int k = 0; k < D_COUNT; k++) detail[k] = 0.0;
-        detail[D_MARGIN_DB] = detail[D_MARGIN_PROB] = detail[D_MARGIN_BYTES] = INFINITY;
+        detail[D_MARGIN_DB] = detail[D_MARGIN_PROB] = detail[D_MARGIN_BYTES] = detail[D_MARGIN_DIST] = INFINITY;
     }
     g_mg = detail;
     double prev_dist = e->prev_dist_nearest;
@@ -663,7 +666,7 @@ void orc_reset_batch(const orc_params* p, orc_env* envs, int e0, int e1, const d
     for (int e = e0; e < e1; e++) {
         if (detail) {
             g_mg = detail + (size_t)e * D_COUNT;
-            g_mg[D_MARGIN_DB] = g_mg[D_MARGIN_PROB] = g_mg[D_MARGIN_BYTES] = INFINITY;
+            g_mg[D_MARGIN_DB] = g_mg[D_MARGIN_PROB] = g_mg[D_MARGIN_BYTES] = g_mg[D_MARGIN_DIST] = INFINITY;
         }
         orc_reset_env(p, &envs[e], fill ? fill + (size_t)e * P : NULL, draws + (size_t)e * ORC_SLOTS * P, P,
                       init_sf ? init_sf[e] : 0, obs + (size_t)e * dim, mask ? mask + e : NULL);

@@ -85,7 +85,7 @@ inline void launch_step_kernel(Kernel k, size_t smem, int warps, bool min4, cons
 
 // Throughput build, Philox, no diagnostics: the plain UAVEnvironment step, the DomainRandEnv training step and the
 // RelationalUAVEnv step run LEAN instantiations (the features they do not use are compiled out, finished episodes restart
-// in a second launch); everything else takes the generic kernel.
+// outside the tile loop); everything else takes the generic kernel.
 template <typename Real>
 inline bool lean_eligible(const Params<Real>& p, const Buffers& b, bool replay) {
 #ifdef UAVSIM_NO_LEAN
@@ -96,10 +96,10 @@ inline bool lean_eligible(const Params<Real>& p, const Buffers& b, bool replay) 
            !(p.wind_drift > 0.0) && ((p.fps == 3 && !p.relational) || (p.fps == 5 && p.relational && !p.domain_rand));
 #endif
 }
-// Kernels one step launches: the LEAN kernels hand finished episodes to restart_kernel.
+// Kernels one step launches.
 template <typename Real>
-inline int step_launch_count(const Params<Real>& p, const Buffers& b, bool replay) {
-    return lean_eligible(p, b, replay) && p.auto_reset ? 2 : 1;
+inline int step_launch_count(const Params<Real>&, const Buffers&, bool) {
+    return 1;
 }
 
 template <typename Real>
@@ -114,15 +114,11 @@ inline cudaError_t launch_step_t(const Params<Real>& p, const Buffers& b, const 
             Buffers bb;
 #define UAVSIM_LAUNCH_LEAN(S, F, MODE, PAIRED)                                                                   \
     do {                                                                                                      \
-        constexpr size_t smem = step_smem_bytes<Real, S, PAIRED, true>();                                     \
+        constexpr size_t smem = step_smem_bytes<Real, S, PAIRED>();                                           \
         constexpr int warps = step_warps<Real, S, PAIRED>();                                                  \
         auto k = stack ? step_kernel<Real, false, S, F, true, MODE, PAIRED> : step_kernel<Real, false, S, F, false, MODE, PAIRED>; \
         launch_step_kernel(k, smem, warps, true, b, &grid, &bb);                                            \
         k<<<grid, 32 * warps, smem, st>>>(p, bb, actions);                                                    \
-        if (p.auto_reset) { /* finished episodes restart in their own launch (uavsim_step.cuh, restart_kernel) */ \
-            auto rk = restart_kernel<Real, false, S, F>;                                                      \
-            rk<<<persistent_grid(rk, (b.E + 31) / 32), kThreads, 0, st>>>(p, bb);                             \
-        }                                                                                                     \
     } while (0)
             if (p.relational) {  // RelationalUAVEnv rows (5 features per sensor)
                 if (two)

@@ -776,11 +776,34 @@ __device__ __forceinline__ void pair_phase(const Params<float>& p, const Buffers
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) s[q].det = det_rssi(p, ts.x[k0 + q], ts.y[k0 + q], s[q].sx, s[q].sy);
+#ifndef UAVSIM_PAIR_FOLD  // the collect path inlined once per slot; -DUAVSIM_PAIR_FOLD: one copy (3 % slower, measured)
 #pragma unroll
     for (int q = 0; q < 2; ++q)
         if (valid[q] && collect[q])
             collect_action<float, false, 1, LEAN>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(s[q]),
                                                   step_loss[q], lane);
+#else
+    {   // A/B variant: ONE copy of the collect path for both slots, the collecting slot selected into a temporary (at most
+        // two rounds).  840 SASS instructions shorter, but 0.426 vs 0.413 ms per launch at N = 20: rejected.
+        const bool c0 = valid[0] && collect[0], c1 = valid[1] && collect[1];
+        if (c0 || c1) {
+            int q = c0 ? 0 : 1;
+            for (;;) {
+                Sensor<float> t = q ? s[1] : s[0];
+                collect_action<float, false, 1, LEAN>(p, b, ts, ws, k0 + q, base + k0 + q, reinterpret_cast<View>(t),
+                                                      q ? step_loss[1] : step_loss[0], lane);
+                if (q)
+                    s[1] = t;
+                else
+                    s[0] = t;
+                if (q == 0 && c1)
+                    q = 1;
+                else
+                    break;
+            }
+        }
+    }
+#endif
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         if (flags[q] & kFlagTruncated) {  // reward_function.py:59-67
@@ -826,18 +849,19 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
                 const int32_t* __restrict__ actions) {
     constexpr bool kParity = std::is_same<Real, double>::value;
     constexpr bool kStaged = !kParity;  // the float32 layout runs the cp.async software pipeline
-    // LEAN instantiations leave finished episodes to restart_kernel (launched right behind this one on the same
-    // stream): the out-of-line restart path -- episode statistics, terminal info, DomainRandEnv scenario draws with
-    // the far-start search, first observation -- costs the hot loop registers and instruction cache even though it
-    // almost never runs (the terminal-info call alone: 0.65 -> 0.74 ms per launch at N = 50, profiles/README.md).
+    // LEAN instantiations restart finished episodes OUTSIDE the tile loop: a tile that ends episodes leaves the loop
+    // with the mask of its finished environments, they are restarted (out-of-line call), and the loop is re-entered.
+    // The restart path -- episode statistics, terminal info, DomainRandEnv scenario draws with the far-start search,
+    // first observation -- almost never runs, but a call to it INSIDE the hot loop costs the loop registers at the call
+    // site: adding one more callee to it (the terminal-info row) took the N = 50 step from 0.65 to 0.74 ms per launch
+    // (profiles/README.md).  (Round 2 first moved it to a second launch: 30-38 us per step on the critical path.)
     constexpr bool kDeferredRestart = LEAN != kGeneric;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(!PAIR || ((LEAN == kLeanPlain || LEAN == kLeanDomainRand) && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
                   "the pair kernel is the plain throughput step with one sensor slot per lane");
-    constexpr bool kNoWs = LEAN != kGeneric && !std::is_same<Real, double>::value;
-    StepWarpSmem<Real, SPL, PAIR, kNoWs>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR, kNoWs>*>(dyn_smem)[warp];
-    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(&mine);  // kNoWs: a name only -- nothing in these instantiations touches it
+    StepWarpSmem<Real, SPL, PAIR>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR>*>(dyn_smem)[warp];
+    WarpSmem& ws = mine.ws[0];
     TileSmem<Real>& ts = mine.ts;
     StageBuf<Real, SPL>* stage = mine.stage;
     // loop-invariant scalars are re-derived from the constant bank where they are used instead of being
@@ -882,7 +906,10 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         }
     }
 
-    while (base < UAVSIM_E) {
+    unsigned pend_mask = 0u;  // finished environments of the tile that has just left the loop (kDeferredRestart)
+    int pend_base = 0;
+  for (;;) {
+    while (base < UAVSIM_E && pend_mask == 0u) {
         const int pending_ticket = UAVSIM_TAKE_TICKET();  // the tile after the next one; consumed at the end of this tile
         const int ntile = min(b.tile, UAVSIM_E - base);
         uint32_t(*rec)[32] = ts.rec[tb];
@@ -911,7 +938,6 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
             if (masked_out) {
             } else if (my_action < 0 || my_action > 4) {  // uav_env.py:468 raises ValueError; here: flag it, leave the env untouched
                 atomicMin(b.error_word, ((unsigned long long)b.step_serial << 32) | (unsigned)e);
-                if constexpr (kDeferredRestart) b.done[e] = 0;  // restart_kernel goes by the done flags of THIS step
             } else {
                 my_flags = kFlagValid;
                 float x = R.f(kRX), y = R.f(kRY);
@@ -1240,7 +1266,11 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         __syncwarp();
 
         // ---- SB3 VecEnv semantics: finished episodes restart inside the same call (rare) ----
-        if constexpr (kDeferredRestart) restart_mask = 0u;
+        if constexpr (kDeferredRestart) {
+            pend_mask = restart_mask;
+            pend_base = base;
+            restart_mask = 0u;
+        }
         while (restart_mask) {
             const int k = __ffs(restart_mask) - 1;
             restart_mask &= restart_mask - 1;
@@ -1268,6 +1298,18 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
         base = next_base;
         next_base = (int)__reduce_max_sync(kFull, (unsigned)pending_ticket) * b.tile;
     }
+    if constexpr (kDeferredRestart) {
+        while (pend_mask) {  // the tile's records are back in global memory: restart straight from there
+            const int e = pend_base + __ffs(pend_mask) - 1;
+            pend_mask &= pend_mask - 1;
+            load_record(ws, b.rec + e, lane);
+            finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
+            store_record(ws, b.rec + e, lane);
+            __syncwarp();
+        }
+    }
+    if (!(base < UAVSIM_E)) break;
+  }
     // every warp of this block has drawn its last ticket; the last block to get here resets the counters
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1281,29 +1323,6 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
 #undef UAVSIM_E
 #undef UAVSIM_NEXT_BASE
 #undef UAVSIM_TAKE_TICKET
-}
-
-// Finished episodes of the step just launched (done flag set): terminal observation, episode statistics, terminal
-// info, new episode -- DummyVecEnv's reset-on-done, for the LEAN step kernels.  One warp per finished environment;
-// a warp scans 32 done flags at a time.
-template <typename Real, bool REPLAY, int SPL, int FPS>
-__global__ void __launch_bounds__(kThreads) restart_kernel(const __grid_constant__ Params<Real> p, const __grid_constant__ Buffers b) {
-    __shared__ WarpSmem smem[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& ws = smem[warp];
-    const int nchunks = (b.E + 31) / 32;
-    for (int c = blockIdx.x * kWarpsPerBlock + warp; c < nchunks; c += gridDim.x * kWarpsPerBlock) {
-        const int e0 = c * 32 + lane;
-        unsigned m = __ballot_sync(kFull, e0 < b.E && b.done[e0] != 0);
-        while (m) {
-            const int e = c * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            load_record(ws, b.rec + e, lane);
-            finish_and_restart<Real, REPLAY, SPL, FPS>(p, b, e, lane, ws);
-            store_record(ws, b.rec + e, lane);
-            __syncwarp();
-        }
-    }
 }
 
 }  // namespace uavsim

@@ -149,3 +149,34 @@ def test_step_is_capturable_in_a_cuda_graph(pkg):
     assert torch.equal(eager.stat_sums[-1], graphed.stat_sums[-1]) and int(eager.stat_sums[-1].item()) > 0
     eager.close()
     graphed.close()
+
+
+@pytest.mark.parametrize("n_sensors,n_stack", [(20, 1), (50, 1), (20, 4)])
+def test_pipelined_host_step_equals_one_launch(pkg, n_sensors, n_stack):
+    """uavsim_step_host steps a big batch as 4 env ranges (copy-out of range k overlapping the step of range k+1).
+    Environments are independent and their draws are keyed by the global env id, so the result must be bit-identical
+    to stepping the whole batch in one launch -- observations, rewards, dones, restarts, episode statistics."""
+    import torch
+    E = 70016 + 40                      # not a multiple of the 64-env range granularity
+    kw = dict(grid_size=(300, 300), num_sensors=n_sensors, seed=17, max_battery=1.2, n_stack=n_stack)
+    a, b = pkg.UAVVecEnv(E, **kw), pkg.UAVVecEnv(E, **kw)
+    a.reset_tensors()
+    b.reset_tensors()
+    host = a.make_host_buffers()
+    g = torch.Generator()
+    g.manual_seed(5)
+    dones = 0
+    for t in range(12):
+        act = torch.randint(0, 5, (E,), dtype=torch.int32, generator=g)
+        host["actions"].copy_(act)
+        obs, rew, done = a.step_host(host)                      # 4 ranges, second stream
+        b.step_tensors(act.to(b.device))                        # one launch
+        assert torch.equal(obs, b.obs.cpu()), t
+        assert torch.equal(rew, b.reward.cpu()) and torch.equal(done, b.done.cpu()), t
+        dones += int(done.sum())
+    assert dones > 1000
+    assert torch.equal(a.terminal_obs, b.terminal_obs) and torch.equal(a.episode_stats, b.episode_stats)
+    assert torch.allclose(a.stat_sums, b.stat_sums, rtol=1e-12)
+    assert a.launch_count - b.launch_count == 12 * 3            # 4 launches per step instead of 1
+    a.close()
+    b.close()

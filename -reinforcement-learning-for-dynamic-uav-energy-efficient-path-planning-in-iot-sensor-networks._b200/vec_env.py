@@ -57,13 +57,10 @@ def numa_local_cpus(dev_index: int):
     """(CPUs of the NUMA node the GPU hangs off that this process may run on, node id) from sysfs; (None, node) when
     the topology cannot be read or the cpuset excludes that node."""
     import os
-    import subprocess
     from pathlib import Path
     try:
-        bus = subprocess.run(["nvidia-smi", "-i", str(dev_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
-        if len(bus.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit PCI domain, sysfs a 4-digit one
-            bus = bus[4:]
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         node = int(Path("/sys/bus/pci/devices/%s/numa_node" % bus).read_text())
         if node < 0:
             return None, node

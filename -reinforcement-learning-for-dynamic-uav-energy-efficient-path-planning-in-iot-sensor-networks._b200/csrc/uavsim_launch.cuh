@@ -63,13 +63,20 @@ inline int persistent_grid(Kernel k, int E, size_t dyn_smem = 0, int envs_per_wa
     return need < blocks_per_wave ? need : blocks_per_wave;
 }
 
-// Environments per tile of a step launch: 16 when every resident warp gets at least ~2.5 tiles, else the largest
-// smaller tile that does (phases A / C run one environment per lane, so a smaller tile costs a few per cent per
-// environment but lets a small batch use the whole machine).  The staged (float32) kernels prefetch two
-// environments / one pair ahead across tile boundaries and need a multiple of 4.
+// Environments per tile of a step launch: 16 when every resident warp gets at least ~2.5 tiles, else the largest smaller
+// tile that does (phases A / C run one environment per lane, so a smaller tile costs a few per cent per environment but
+// lets a small batch use the whole machine).  The staged (float32) kernels prefetch two environments / one pair ahead
+// across tile boundaries and need a multiple of 4.  UAVSIM_TILES_PER_WARP overrides the 2.5 for sweeps; measured flat:
+// a 131,072-env shard (strong scaling over 8 GPUs) takes 0.109 / 0.105 / 0.113 ms at 2.5 / 5 / 8 tiles per warp, so the
+// 30 % such a shard loses against the 1 M-env rate is launch + pipeline ramp, not the tile tail
+// (profiles/r02d_tiles_per_warp_ab.txt).
+inline double tiles_per_warp_target() {
+    static const double v = getenv("UAVSIM_TILES_PER_WARP") ? atof(getenv("UAVSIM_TILES_PER_WARP")) : 2.5;
+    return v;
+}
 inline int choose_tile(int E, int resident_warps, bool min4) {
     for (int t = kTile; t >= (min4 ? 4 : 2); t >>= 1)
-        if ((double)E >= 2.5 * (double)t * (double)resident_warps) return t;
+        if ((double)E >= tiles_per_warp_target() * (double)t * (double)resident_warps) return t;
     return min4 ? 4 : 2;
 }
 

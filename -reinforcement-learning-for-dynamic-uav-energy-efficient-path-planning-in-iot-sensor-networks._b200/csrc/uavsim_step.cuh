@@ -496,17 +496,15 @@ struct alignas(16) TileSmem {
 
 // Dynamic shared memory of one block of the step kernel: per warp a working record + reduction scratch,
 // the tile block and (float32 layout) two stage buffers.
-// NOWS: the float32 LEAN kernels use neither the working record (their restarts run in restart_kernel) nor the ordered-
-// reduction scratch (parity build only): 640 B per warp less.
-template <typename Real, int SPL, bool PAIR = false, bool NOWS = false>
+template <typename Real, int SPL, bool PAIR = false>
 struct alignas(alignof(SensorState<Real>) > 16 ? alignof(SensorState<Real>) : 16) StepWarpSmem {
-    WarpSmem ws[NOWS ? 0 : 1];
+    WarpSmem ws;
     TileSmem<Real> ts;
     StageBuf<Real, SPL> stage[std::is_same<Real, double>::value ? 0 : (PAIR ? 4 : 2)];  // pair kernel: 2 stages x 2 envs
 };
-template <typename Real, int SPL, bool PAIR = false, bool NOWS = false>
+template <typename Real, int SPL, bool PAIR = false>
 constexpr size_t step_smem_bytes() {
-    return sizeof(StepWarpSmem<Real, SPL, PAIR, NOWS>) * step_warps<Real, SPL, PAIR>();
+    return sizeof(StepWarpSmem<Real, SPL, PAIR>) * step_warps<Real, SPL, PAIR>();
 }
 
 enum : int {
@@ -861,7 +859,7 @@ __global__ void __launch_bounds__(32 * step_warps<Real, SPL, PAIR>(), step_min_b
     static_assert(!PAIR || ((LEAN == kLeanPlain || LEAN == kLeanDomainRand) && SPL == 1 && FPS == 3 && !REPLAY && !std::is_same<Real, double>::value),
                   "the pair kernel is the plain throughput step with one sensor slot per lane");
     StepWarpSmem<Real, SPL, PAIR>& mine = reinterpret_cast<StepWarpSmem<Real, SPL, PAIR>*>(dyn_smem)[warp];
-    WarpSmem& ws = mine.ws[0];
+    WarpSmem& ws = mine.ws;
     TileSmem<Real>& ts = mine.ts;
     StageBuf<Real, SPL>* stage = mine.stage;
     // loop-invariant scalars are re-derived from the constant bank where they are used instead of being

@@ -16,7 +16,8 @@ of the rank.
            uavsim_step_host): actions copied host->device and obs/reward/done copied device->host
            inside the timed region, every step.
 `roofline`: algorithmic bytes per env-step x envs per launch / mean launch duration,
-           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json (also on SURVEY 8d's byte model).
+`sustained`, `strong_scaling`, `secondary_*`, `e2e.pcie_roofline`: see DESIGN.md section 5.
 `cpu_baseline`: the reference's algorithm on the box's host cores (python port of the reference's
            per-sensor numpy-scalar step, all cores, bounded sample) -- a reported baseline.
 
@@ -41,7 +42,7 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = dict(name="configs[4]: scalability sweep 1000x1000, N=50, 1M envs per GPU, random actions, Philox",
                 grid=(1000, 1000), num_sensors=50, envs_per_gpu=1 << 20)
 METRIC = "env-steps/sec"
-KERNEL_NAME = "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=plain%s> (+ restart_kernel for finished episodes, same stream)"
+KERNEL_NAME = "uavsim::step_kernel<float, REPLAY=false, SPL=%d, FPS=3, STACK=false, LEAN=plain%s>"
 
 
 def bytes_per_env_step(n_sensors: int, precision: str = "f32", obs_floats: int | None = None) -> int:
@@ -383,7 +384,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         bpe = bytes_per_env_step(n, "f32")
-        launch_ms = ms_max / args.steps      # per step: the step kernel + the restart kernel behind it (a few us)
+        launch_ms = ms_max / max(launches, 1)   # one step kernel per step (finished episodes restart inside it)
         achieved = bpe * E / (launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tpath = ROOT / "profiles" / "dram_traffic.json"
